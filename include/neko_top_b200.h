@@ -1,0 +1,171 @@
+/*
+ * neko_top_b200.h -- C ABI of the B200-native adjoint-RHS path for Neko-TOP.
+ *
+ * Drop-in boundary for SURVEY.md section 8 rows (a1)-(a12): every entry point is `extern "C"`,
+ * takes plain pointers and sizes (no C++ / torch types), and follows the calling convention of the
+ * reference's own CUDA shims so that a Fortran `bind(c)` interface block binds it directly:
+ *   - device pointers are passed BY VALUE as `void*`   (Fortran: `type(c_ptr), value`)
+ *   - scalars are passed BY REFERENCE                  (Fortran: `integer(c_int) :: n`, `real(c_rp) :: c`)
+ *   - masks are 1-based linear indices                 (math_ext_kernel.h:49 `a[mask[i]-1]`)
+ * exactly as /root/reference/sources/neko_ext/math/bcknd/device_math_ext.f90:43-103 binds
+ * /root/reference/sources/neko_ext/math/bcknd/device/cuda/math_ext.cu:49-108.
+ * Fields are fp64 (Neko `rp` = `dp`), Fortran column-major x(lx,lx,lx,nelv).
+ *
+ * Error convention (reference: neko_error / CUDA_CHECK abort the job, math_ext.cu:56): every call
+ * returns 0 on success; on failure it prints the reason to stderr and, unless
+ * b200_set_abort_on_error(0) was called, aborts -- there is no CPU fallback anywhere.
+ *
+ * All citations are relative to /root/reference/sources.
+ */
+#ifndef NEKO_TOP_B200_H
+#define NEKO_TOP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG 1
+#define B200_ERR_CUDA 2
+#define B200_ERR_NCCL 3
+#define B200_ERR_STATE 4
+
+/* library-wide */
+int b200_version(void);
+void b200_set_abort_on_error(const int* flag);
+const char* b200_last_error(void);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+int64_t b200_launch_count(void);
+
+/* ---- handle: one per (space, mesh partition) == one per Neko `coef_t` -----------------------
+ * replaces the state held by adv_lin_no_dealias_t (adjoint/adv_adjoint_no_dealias.f90:57-77)
+ * and adv_lin_dealias_t (adjoint/adv_adjoint_dealias.f90:56-131). */
+int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int* device);
+int b200_adjrhs_free(void** handle);
+/* Neko enqueues everything on glb_cmd_queue (math_ext.cu:54); pass it here (NULL = default). */
+int b200_adjrhs_set_stream(void* handle, void* stream);
+/* space_t: dx = Xh%dx (lx*lx, column-major D(i,j)), wx = Xh%wx (lx); HOST pointers. */
+int b200_adjrhs_set_space(void* handle, const double* dx, const double* wx);
+/* coef_t device mirrors: coef%drdx_d ... coef%dtdz_d (cofactors, J-scaled) and coef%B_d.
+ * Borrowed; must stay valid while the handle is used. */
+int b200_adjrhs_set_geometry(void* handle,
+                             const void* drdx, const void* dsdx, const void* dtdx,
+                             const void* drdy, const void* dsdy, const void* dtdy,
+                             const void* drdz, const void* dsdz, const void* dtdz,
+                             const void* B);
+/* RAMP constants (mapping_functions/RAMP_mapping.f90:107-110), lube K*obj_scale and the
+ * sensitivity K*obj_scale (objectives/minimum_dissipation_objective_function.f90:131-133). */
+int b200_adjrhs_set_params(void* handle, const double* f_min, const double* f_max, const double* q,
+                           const int* convex_up, const int* if_lube, const double* K_lube,
+                           const double* K_sens);
+/* optional point-zone mask of the lube term (source_terms/adjoint_lube_source_term.f90:196-198,
+ * neko_ext/mask_ops.f90:55-82): DEVICE array of 1-based indices; mask_size = 0 disables. */
+int b200_adjrhs_set_lube_mask(void* handle, const void* mask_d, const int* mask_size);
+
+/* ---- the fused path: adjoint/adjoint_pnpn.f90:669-682 in one pass per element ---------------
+ *   chi = RAMP(rho)            (rho != NULL; else chi taken from chi_in; both NULL: no source terms)
+ *   f_i = B*(-chi*v_i [+K_lube*chi*vb_i] [+fs_i]) - adjoint advection(v, vb)
+ *   sens = -(vb.v) + K_sens*(vb.vb)        (sens != NULL)
+ * f is WRITE-ONLY here.  All pointers are device pointers; optional ones may be NULL. */
+int b200_adjrhs_compute(void* handle,
+                        const void* vx, const void* vy, const void* vz,
+                        const void* vxb, const void* vyb, const void* vzb,
+                        const void* rho, const void* chi_in,
+                        const void* fsx, const void* fsy, const void* fsz,
+                        void* fx, void* fy, void* fz,
+                        void* sens, void* chi_out);
+/* fused path followed by gs_op(f_i, GS_OP_ADD) on the three components
+ * (adjoint_pnpn.f90:755-757); needs b200_gs_init.  This is one "step" of bench.py. */
+int b200_adjrhs_step(void* handle,
+                     const void* vx, const void* vy, const void* vz,
+                     const void* vxb, const void* vyb, const void* vzb,
+                     const void* rho, const void* chi_in,
+                     const void* fsx, const void* fsy, const void* fsz,
+                     void* fx, void* fy, void* fz,
+                     void* sens, void* chi_out);
+/* same step with HOST buffers (each n doubles): H2D of v, vb, rho; D2H of f, sens; staged through
+ * pinned memory in element chunks so copies overlap the kernels.  Geometry stays device-resident
+ * (it is set once, like coef_t).  This is bench.py's "e2e". */
+int b200_adjrhs_step_host(void* handle,
+                          const double* vx, const double* vy, const double* vz,
+                          const double* vxb, const double* vyb, const double* vzb,
+                          const double* rho,
+                          double* fx, double* fy, double* fz, double* sens);
+
+/* ---- un-fused drop-ins, one per reference plug-in method -----------------------------------
+ * advection_adjoint_t%compute_adjoint (adjoint/advection_adjoint.f90:67-81; implementation
+ * adjoint/adv_adjoint_no_dealias.f90:119-255): f is IN/OUT, accumulated. */
+int b200_adv_adjoint_compute(void* handle,
+                             const void* vx, const void* vy, const void* vz,
+                             const void* vxb, const void* vyb, const void* vzb,
+                             void* fx, void* fy, void* fz);
+/* advection_adjoint_t%compute_linear (adjoint/adv_adjoint_no_dealias.f90:365-427); needs jacinv. */
+int b200_adv_linear_compute(void* handle,
+                            const void* vx, const void* vy, const void* vz,
+                            const void* vxb, const void* vyb, const void* vzb,
+                            const void* jacinv,
+                            void* fx, void* fy, void* fz);
+/* simple_brinkman_source_term_t%compute_ (source_terms/simple_brinkman_source_term.f90:139-153):
+ * f_i -= chi*u_i */
+int b200_brinkman_compute(void* fu, void* fv, void* fw, const void* u, const void* v, const void* w,
+                          const void* chi, const int* n, void* stream);
+/* adjoint_lube_source_term_t%compute_ (source_terms/adjoint_lube_source_term.f90:173-206):
+ * f_i += K*chi*u_i on the mask (mask_size = 0: everywhere) */
+int b200_lube_compute(void* fu, void* fv, void* fw, const void* u, const void* v, const void* w,
+                      const void* chi, const double* K, const void* mask_d, const int* mask_size,
+                      const int* n, void* stream);
+/* opcolv (adjoint/adjoint_pnpn.f90:672-676): f_i *= B */
+int b200_opcolv(void* fx, void* fy, void* fz, const void* B, const int* n, void* stream);
+/* RAMP_mapping_t%apply_forward / apply_backward (mapping_functions/RAMP_mapping.f90:137-267) */
+int b200_ramp_forward(void* chi, const void* rho, const int* n, const double* f_min,
+                      const double* f_max, const double* q, const int* convex_up, void* stream);
+int b200_ramp_backward(void* dF_drho, const void* dF_dchi, const void* rho, const int* n,
+                       const double* f_min, const double* f_max, const double* q,
+                       const int* convex_up, void* stream);
+/* minimum_dissipation_objective_function_t%compute_sensitivity
+ * (objectives/minimum_dissipation_objective_function.f90:260-301) */
+int b200_sensitivity(void* sens, const void* u, const void* v, const void* w, const void* ua,
+                     const void* va, const void* wa, const double* K_obj, const int* if_lube,
+                     const int* n, void* stream);
+/* steady_simcomp_t%compute_ (simulation_components/steady_simcomp.f90:158-188), one field per call:
+ * *result = sum_i (x_old - x)^2 (the local part of field_sub2 + field_glsc2) and x_old <- x
+ * (field_copy), in one pass.  Synchronises the stream (it returns a host scalar). */
+int b200_steady_field_update(double* result, const void* x, void* x_old, const int* n, void* stream);
+
+/* ---- gather-scatter: gs_t%op(., GS_OP_ADD) (adjoint/adjoint_pnpn.f90:725,755-757) ------------
+ * key: global node id of every local dof (n = nelv*lx^3 int64), device pointer if *on_device.
+ * Two dofs are summed iff their keys are equal (SURVEY.md 8c "node equivalence classes"). */
+int b200_gs_init(void* handle, const int64_t* key, const int* on_device);
+/* parity hook: class id per dof, classes numbered by ascending smallest member dof (the same
+ * canonical relabelling the oracle uses); HOST output, n int64. Returns #classes in *nclass. */
+int b200_gs_get_classes(void* handle, int64_t* class_id, int64_t* nclass);
+int b200_gs_op(void* handle, void* f);                       /* one field   */
+int b200_gs_op3(void* handle, void* fx, void* fy, void* fz); /* three fields, one pass */
+
+/* ---- multi-GPU: one process per GPU, shared-node exchange as NCCL send/recv over NVLink -------
+ * id: 128-byte ncclUniqueId made by rank 0 (b200_comm_unique_id) and distributed by the host
+ * (MPI_Bcast in Neko, torch.distributed in bench.py). */
+int b200_comm_unique_id(char* id128);
+int b200_comm_init(void* handle, const char* id128, const int* rank, const int* nranks);
+/* shared nodes, as Neko's gs_t stores them (shared dofs + per-neighbour lists):
+ *   nshared          number of local node classes that also live on other ranks
+ *   shared_dof[s]    0-based local dof index of any member of class s
+ *   nneigh, neigh_rank[j], neigh_off[j..j+1], neigh_idx[...]: for neighbour j the indices s (into
+ *   shared_dof) of the nodes shared with it, in an order both sides agree on (ascending key). */
+int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof, const int* nneigh,
+                        const int* neigh_rank, const int* neigh_off, const int* neigh_idx);
+/* elements that own a shared node (computed first so the exchange overlaps the interior ones) */
+int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* bnd_elem);
+
+/* ---- diagnostics ----------------------------------------------------------------------------*/
+/* average device time (ms) of the last fused element-kernel launches measured with CUDA events
+ * on the handle's stream when profiling is enabled; used by bench.py's roofline block */
+int b200_adjrhs_enable_timing(void* handle, const int* flag);
+int b200_adjrhs_get_timing(void* handle, double* elem_kernel_ms, double* gs_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

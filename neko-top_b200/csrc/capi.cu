@@ -1,0 +1,1038 @@
+// C ABI of the B200-native adjoint-RHS path (see include/neko_top_b200.h for the contract and the
+// reference interfaces each entry point replaces).  No CPU fallback: every compute entry point
+// launches sm_100a kernels or fails loudly.
+#include "../../include/neko_top_b200.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "adjrhs_kernel.cuh"
+#include "gs_kernels.cuh"
+#include "pointwise_kernels.cuh"
+
+namespace {
+
+using namespace b200;
+
+std::atomic<int64_t> g_launches{0};
+int g_abort = 1;
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  fprintf(stderr, "[neko_top_b200] ERROR: %s\n", buf);
+  if (g_abort) abort();   // reference convention: neko_error / CUDA_CHECK end the job
+  return code;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(B200_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                  cudaGetErrorString(e_));                                                        \
+  } while (0)
+#define NK(call)                                                                                  \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess)                                                                        \
+      return fail(B200_ERR_NCCL, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                  ncclGetErrorString(r_));                                                        \
+  } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+constexpr int LX_MAX = 10;
+
+struct Handle {
+  int lx = 0, nelv = 0, device = 0;
+  int64_t n = 0;
+  int num_sm = 0;
+  cudaStream_t stream = nullptr;
+  bool have_space = false, have_geom = false;
+  double D[LX_MAX * LX_MAX];
+  double w[LX_MAX];
+  const double* G[9] = {};
+  const double* B = nullptr;
+  double f_min = 0.0, f_max = 1000.0, q = 1.0, K_lube = 1.0, K_sens = 1.0;
+  int convex_up = 1, if_lube = 1;
+  const int* lube_mask = nullptr;
+  int lube_mask_size = 0;
+  int cfg = -1;   // kernel configuration override (B200_ADJRHS_CFG)
+
+  // gather-scatter
+  bool have_gs = false;
+  int nclass = 0;
+  int64_t nmember = 0;
+  int *gs_off = nullptr, *gs_dof = nullptr, *gs_rep = nullptr;
+  unsigned char* gs_skip = nullptr;     // classes handled by the shared-node path
+  int* gs_shared_cls = nullptr;         // list of local classes that contain a shared node
+  int n_shared_cls = 0;
+
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_recv = nullptr;
+  int nshared = 0, nneigh = 0;
+  std::vector<int> neigh_rank, neigh_off;
+  int *d_send_dof = nullptr, *d_shared_dof = nullptr, *d_s_class = nullptr, *d_c_off = nullptr,
+      *d_c_src = nullptr;
+  double *d_send = nullptr, *d_recv = nullptr;
+  int nsend = 0;
+  int *d_bnd_elem = nullptr, *d_int_elem = nullptr;
+  int nbnd = 0, nint = 0;
+
+  // host-staged step
+  double* stage[11] = {};
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> ev_h2d, ev_k;
+  cudaEvent_t ev_done = nullptr;
+
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;   // (start, mid, end) triples: elem kernel = mid-start, gs = end-mid
+};
+
+Handle* H(void* h) { return reinterpret_cast<Handle*>(h); }
+
+int grid_for(int64_t n, int threads, int num_sm, int per_sm) {
+  int64_t need = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sm * per_sm;
+  return (int)std::max<int64_t>(1, std::min(need, cap));
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused element kernel launcher
+// ---------------------------------------------------------------------------------------------
+struct LaunchArgs {
+  const double* v[3];
+  const double* vb[3];
+  const double* rho;      // rho or chi
+  bool rho_is_chi;
+  const double* fs[3];
+  const double* fin[3];   // accumulate mode
+  double* f[3];
+  double* sens;
+  double* chi_out;
+  const int* elem_list;
+  int nelem;
+  int elem_begin;         // used only when elem_list == nullptr (via pointer offsets)
+  bool sources;
+};
+
+template <int LX, int PC, int NS, int NU, int MAXREG>
+int launch_cfg(Handle* h, const LaunchArgs& a) {
+  using L = SmemLayout<LX, PC, NS, NU>;
+  using C = KernelCfg<LX, PC, NS, NU>;
+  KParams<LX> p;
+  memset(&p, 0, sizeof p);
+  for (int i = 0; i < LX * LX; i++) p.D[i] = h->D[i];
+  for (int i = 0; i < LX; i++) p.w[i] = h->w[i];
+  const size_t eoff = (size_t)a.elem_begin * L::N;
+  for (int c = 0; c < 3; c++) p.ub[c] = a.vb[c] + eoff;
+  for (int i = 0; i < PF_COUNT; i++) { p.pf[i] = nullptr; p.pf_slot[i] = -1; }
+  unsigned flags = 0;
+  int np = 0;
+  auto add = [&](int slot, const double* ptr) { p.pf[slot] = ptr + eoff; p.pf_slot[slot] = np++; };
+  for (int c = 0; c < 3; c++) add(PF_VX + c, a.v[c]);
+  for (int g = 0; g < 9; g++) add(PF_G0 + g, h->G[g]);
+  const bool need_B = a.sources || a.fs[0];
+  if (need_B) add(PF_B, h->B);
+  if (a.sources) {
+    add(PF_RHO, a.rho);
+    flags |= FLAG_SOURCES;
+    if (!a.rho_is_chi) flags |= FLAG_RAMP;
+    if (h->convex_up) flags |= FLAG_CONVEX_UP;
+    if (h->if_lube && h->lube_mask_size == 0) flags |= FLAG_LUBE;
+    if (a.chi_out) flags |= FLAG_CHI_OUT;
+  }
+  if (a.fs[0]) { for (int c = 0; c < 3; c++) add(PF_FS0 + c, a.fs[c]); flags |= FLAG_FSTATIC; }
+  if (a.fin[0]) { for (int c = 0; c < 3; c++) add(PF_FIN0 + c, a.fin[c]); flags |= FLAG_ACCUM; }
+  if (a.sens) flags |= FLAG_SENS;
+  p.n_pf = np;
+  for (int c = 0; c < 3; c++) p.f[c] = a.f[c] + eoff;
+  p.sens = a.sens ? a.sens + eoff : nullptr;
+  p.chi_out = a.chi_out ? a.chi_out + eoff : nullptr;
+  p.elem_list = a.elem_list;
+  p.nelem = a.nelem;
+  p.flags = flags;
+  p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
+  p.K_sens = h->if_lube ? h->K_sens : 0.0;
+
+  auto kern = adjrhs_fused_kernel<LX, PC, NS, NU, MAXREG>;
+  const int smem = L::total(np);
+  static int smem_set = -1;   // per instantiation
+  if (smem > smem_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHREADS, smem));
+  if (per_sm < 1) return fail(B200_ERR_STATE, "fused kernel does not fit: lx=%d smem=%d", LX, smem);
+  int grid = std::min(a.nelem, h->num_sm * per_sm);
+  if (grid < 1) return B200_OK;
+  kern<<<grid, C::NTHREADS, smem, h->stream>>>(p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int launch_fused(Handle* h, const LaunchArgs& a) {
+  if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
+  const int cfg = h->cfg;
+  switch (h->lx) {
+    case 4: return launch_cfg<4, 2, 2, 2, 224>(h, a);
+    case 5: return launch_cfg<5, 1, 3, 2, 224>(h, a);
+    case 6: return launch_cfg<6, 2, 2, 2, 224>(h, a);
+    case 7: return launch_cfg<7, 1, 3, 2, 224>(h, a);
+    case 8:
+      switch (cfg) {
+        case 1: return launch_cfg<8, 4, 2, 2, 224>(h, a);   // 104 KB, 2 CTA/SM
+        case 2: return launch_cfg<8, 2, 3, 1, 224>(h, a);   //  78 KB, 2 CTA/SM
+        case 3: return launch_cfg<8, 1, 4, 1, 224>(h, a);   //  64 KB, 3 CTA/SM
+        case 4: return launch_cfg<8, 2, 4, 2, 224>(h, a);   // 104 KB, 2 CTA/SM
+        case 5: return launch_cfg<8, 8, 2, 2, 224>(h, a);   // 160 KB, 1 CTA/SM
+        case 6: return launch_cfg<8, 2, 2, 1, 168>(h, a);   //  64 KB, 3 CTA/SM, tighter registers
+        default: return launch_cfg<8, 2, 2, 1, 224>(h, a);  //  64 KB, 3 CTA/SM
+      }
+    case 9: return launch_cfg<9, 1, 3, 1, 224>(h, a);
+    case 10: return launch_cfg<10, 1, 3, 1, 224>(h, a);
+    default: return fail(B200_ERR_ARG, "lx=%d not instantiated (4..10)", h->lx);
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_fields(std::initializer_list<const void*> ps) {
+  for (const void* p : ps)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15) != 0)
+      return fail(B200_ERR_ARG, "device field pointer %p is not 16-byte aligned", p);
+  return B200_OK;
+}
+
+int time_mark(Handle* h) {
+  if (!h->timing) return B200_OK;
+  if (h->tev.size() >= 3 * 4096) return B200_OK;
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(e, h->stream));
+  h->tev.push_back(e);
+  return B200_OK;
+}
+
+// local gather-scatter launches
+int gs_launch(Handle* h, double* f0, double* f1, double* f2, int nf) {
+  if (!h->have_gs) return fail(B200_ERR_STATE, "b200_gs_init not called");
+  if (h->nclass == 0) return B200_OK;
+  const int threads = 256;
+  const int grid = grid_for(h->nclass, threads, h->num_sm, 8);
+  if (nf == 1) gs_op_kernel<1><<<grid, threads, 0, h->stream>>>(f0, f0, f0, h->gs_off, h->gs_dof, h->nclass);
+  else gs_op_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+// shared-node exchange: pack -> ncclSend/Recv (comm stream) -> unpack
+int gs_exchange(Handle* h, double* f0, double* f1, double* f2, int nf) {
+  if (!h->comm || h->nshared == 0) return B200_OK;
+  const int threads = 256;
+  const int grid = grid_for(h->nsend, threads, h->num_sm, 4);
+  if (nf == 1) gs_pack_kernel<1><<<grid, threads, 0, h->stream>>>(f0, f0, f0, h->d_send_dof, h->nsend, h->d_send);
+  else gs_pack_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->d_send_dof, h->nsend, h->d_send);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev_pack, h->stream));
+  CK(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+  NK(ncclGroupStart());
+  for (int j = 0; j < h->nneigh; j++) {
+    const size_t o = (size_t)h->neigh_off[j] * nf, cnt = (size_t)(h->neigh_off[j + 1] - h->neigh_off[j]) * nf;
+    NK(ncclSend(h->d_send + o, cnt, ncclDouble, h->neigh_rank[j], h->comm, h->comm_stream));
+    NK(ncclRecv(h->d_recv + o, cnt, ncclDouble, h->neigh_rank[j], h->comm, h->comm_stream));
+  }
+  NK(ncclGroupEnd());
+  CK(cudaEventRecord(h->ev_recv, h->comm_stream));
+  return B200_OK;
+}
+int gs_finish_exchange(Handle* h, double* f0, double* f1, double* f2, int nf) {
+  if (!h->comm || h->nshared == 0) return B200_OK;
+  CK(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
+  const int threads = 256;
+  const int grid = grid_for(h->nshared, threads, h->num_sm, 4);
+  if (nf == 1)
+    gs_unpack_kernel<1><<<grid, threads, 0, h->stream>>>(f0, f0, f0, h->d_recv, h->d_c_off, h->d_c_src,
+                                                          h->d_shared_dof, h->d_s_class, h->gs_off,
+                                                          h->gs_dof, h->nshared);
+  else
+    gs_unpack_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->d_recv, h->d_c_off, h->d_c_src,
+                                                          h->d_shared_dof, h->d_s_class, h->gs_off,
+                                                          h->gs_dof, h->nshared);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+template <typename T>
+int dmalloc(T** p, size_t count) {
+  CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T)));
+  return B200_OK;
+}
+
+LaunchArgs make_args(const void* vx, const void* vy, const void* vz, const void* vxb, const void* vyb,
+                     const void* vzb, const void* rho, const void* chi_in, const void* fsx,
+                     const void* fsy, const void* fsz, void* fx, void* fy, void* fz, void* sens,
+                     void* chi_out, int nelv) {
+  LaunchArgs a;
+  a.v[0] = (const double*)vx; a.v[1] = (const double*)vy; a.v[2] = (const double*)vz;
+  a.vb[0] = (const double*)vxb; a.vb[1] = (const double*)vyb; a.vb[2] = (const double*)vzb;
+  a.rho = rho ? (const double*)rho : (const double*)chi_in;
+  a.rho_is_chi = (rho == nullptr);
+  a.sources = (a.rho != nullptr);
+  a.fs[0] = (const double*)fsx; a.fs[1] = (const double*)fsy; a.fs[2] = (const double*)fsz;
+  a.fin[0] = a.fin[1] = a.fin[2] = nullptr;
+  a.f[0] = (double*)fx; a.f[1] = (double*)fy; a.f[2] = (double*)fz;
+  a.sens = (double*)sens;
+  a.chi_out = (double*)chi_out;
+  a.elem_list = nullptr;
+  a.nelem = nelv;
+  a.elem_begin = 0;
+  return a;
+}
+
+int masked_lube_post(Handle* h, const LaunchArgs& a) {
+  if (!(a.sources && h->if_lube && h->lube_mask_size > 0)) return B200_OK;
+  const int threads = 256;
+  const int grid = grid_for(h->lube_mask_size, threads, h->num_sm, 4);
+  lube_mask_post_kernel<<<grid, threads, 0, h->stream>>>(a.f[0], a.f[1], a.f[2], a.vb[0], a.vb[1], a.vb[2],
+                                                         a.rho, h->B, h->K_lube, a.rho_is_chi ? 0 : 1,
+                                                         h->convex_up, h->f_min, h->f_max, h->q,
+                                                         h->lube_mask, h->lube_mask_size);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int b200_version(void) { return 100; }
+void b200_set_abort_on_error(const int* flag) { g_abort = flag ? *flag : 1; }
+const char* b200_last_error(void) { return g_err.c_str(); }
+int64_t b200_launch_count(void) { return g_launches.load(); }
+
+int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int* device) {
+  if (!handle || !lx || !nelv) return fail(B200_ERR_ARG, "create: null argument");
+  if (*lx < 4 || *lx > LX_MAX) return fail(B200_ERR_ARG, "create: lx=%d outside 4..%d", *lx, LX_MAX);
+  if (*nelv < 0) return fail(B200_ERR_ARG, "create: nelv=%d", *nelv);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU fallback (%s)", cudaGetErrorString(e));
+  Handle* h = new Handle();
+  h->lx = *lx; h->nelv = *nelv; h->n = (int64_t)(*lx) * (*lx) * (*lx) * (*nelv);
+  if (h->n > 0x7fffffffll) {
+    const long long nn = h->n;
+    delete h;
+    return fail(B200_ERR_ARG, "create: n=%lld exceeds int32 dof indexing", nn);
+  }
+  h->device = device ? *device : 0;
+  CK(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10)
+    fprintf(stderr, "[neko_top_b200] warning: device %s is sm_%d%d, kernels are built for sm_100a\n",
+            prop.name, prop.major, prop.minor);
+  h->num_sm = prop.multiProcessorCount;
+  const char* c = getenv("B200_ADJRHS_CFG");
+  h->cfg = c ? atoi(c) : -1;
+  *handle = h;
+  return B200_OK;
+}
+
+int b200_adjrhs_free(void** handle) {
+  if (!handle || !*handle) return B200_OK;
+  Handle* h = H(*handle);
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep); cudaFree(h->gs_skip);
+  cudaFree(h->gs_shared_cls);
+  cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
+  cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_bnd_elem);
+  cudaFree(h->d_int_elem);
+  for (double* s : h->stage) cudaFree(s);
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_k) cudaEventDestroy(e);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+  if (h->ev_recv) cudaEventDestroy(h->ev_recv);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  if (h->comm) ncclCommDestroy(h->comm);
+  delete h;
+  *handle = nullptr;
+  return B200_OK;
+}
+
+int b200_adjrhs_set_stream(void* handle, void* stream) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  H(handle)->stream = (cudaStream_t)stream;
+  return B200_OK;
+}
+
+int b200_adjrhs_set_space(void* handle, const double* dx, const double* wx) {
+  if (!handle || !dx || !wx) return fail(B200_ERR_ARG, "set_space: null argument");
+  Handle* h = H(handle);
+  memcpy(h->D, dx, sizeof(double) * h->lx * h->lx);
+  memcpy(h->w, wx, sizeof(double) * h->lx);
+  h->have_space = true;
+  return B200_OK;
+}
+
+int b200_adjrhs_set_geometry(void* handle, const void* drdx, const void* dsdx, const void* dtdx,
+                             const void* drdy, const void* dsdy, const void* dtdy, const void* drdz,
+                             const void* dsdz, const void* dtdz, const void* B) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  const void* g[9] = {drdx, dsdx, dtdx, drdy, dsdy, dtdy, drdz, dsdz, dtdz};
+  for (int i = 0; i < 9; i++) {
+    if (!g[i]) return fail(B200_ERR_ARG, "set_geometry: null geometric factor %d", i);
+    h->G[i] = (const double*)g[i];
+  }
+  if (!B) return fail(B200_ERR_ARG, "set_geometry: null B");
+  h->B = (const double*)B;
+  if (int r = check_fields({drdx, dsdx, dtdx, drdy, dsdy, dtdy, drdz, dsdz, dtdz, B})) return r;
+  h->have_geom = true;
+  return B200_OK;
+}
+
+int b200_adjrhs_set_params(void* handle, const double* f_min, const double* f_max, const double* q,
+                           const int* convex_up, const int* if_lube, const double* K_lube,
+                           const double* K_sens) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (f_min) h->f_min = *f_min;
+  if (f_max) h->f_max = *f_max;
+  if (q) h->q = *q;
+  if (convex_up) h->convex_up = *convex_up;
+  if (if_lube) h->if_lube = *if_lube;
+  if (K_lube) h->K_lube = *K_lube;
+  if (K_sens) h->K_sens = *K_sens;
+  return B200_OK;
+}
+
+int b200_adjrhs_set_lube_mask(void* handle, const void* mask_d, const int* mask_size) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  h->lube_mask = (const int*)mask_d;
+  h->lube_mask_size = (mask_d && mask_size) ? *mask_size : 0;
+  return B200_OK;
+}
+
+int b200_adjrhs_compute(void* handle, const void* vx, const void* vy, const void* vz, const void* vxb,
+                        const void* vyb, const void* vzb, const void* rho, const void* chi_in,
+                        const void* fsx, const void* fsy, const void* fsz, void* fx, void* fy, void* fz,
+                        void* sens, void* chi_out) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!vx || !vy || !vz || !vxb || !vyb || !vzb || !fx || !fy || !fz)
+    return fail(B200_ERR_ARG, "compute: null velocity / rhs pointer");
+  if ((fsx || fsy || fsz) && !(fsx && fsy && fsz)) return fail(B200_ERR_ARG, "compute: partial f_static");
+  if (int r = check_fields({vx, vy, vz, vxb, vyb, vzb, rho, chi_in, fsx, fsy, fsz, fx, fy, fz, sens, chi_out}))
+    return r;
+  CK(cudaSetDevice(h->device));
+  LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, rho, chi_in, fsx, fsy, fsz, fx, fy, fz, sens,
+                           chi_out, h->nelv);
+  if (int r = launch_fused(h, a)) return r;
+  return masked_lube_post(h, a);
+}
+
+int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* vz, const void* vxb,
+                     const void* vyb, const void* vzb, const void* rho, const void* chi_in,
+                     const void* fsx, const void* fsy, const void* fsz, void* fx, void* fy, void* fz,
+                     void* sens, void* chi_out) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!h->have_gs) return fail(B200_ERR_STATE, "step: b200_gs_init not called");
+  if (!vx || !vy || !vz || !vxb || !vyb || !vzb || !fx || !fy || !fz)
+    return fail(B200_ERR_ARG, "step: null velocity / rhs pointer");
+  if (int r = check_fields({vx, vy, vz, vxb, vyb, vzb, rho, chi_in, fsx, fsy, fsz, fx, fy, fz, sens, chi_out}))
+    return r;
+  CK(cudaSetDevice(h->device));
+  LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, rho, chi_in, fsx, fsy, fsz, fx, fy, fz, sens,
+                           chi_out, h->nelv);
+  double *f0 = a.f[0], *f1 = a.f[1], *f2 = a.f[2];
+  if (int r = time_mark(h)) return r;
+  const bool split = h->comm && h->nshared > 0 && h->nbnd > 0 && h->n_shared_cls >= 0 && h->gs_skip;
+  if (split) {
+    // boundary elements first, their shared nodes summed locally, packed and sent while the interior
+    // elements are computed
+    LaunchArgs ab = a; ab.elem_list = h->d_bnd_elem; ab.nelem = h->nbnd;
+    if (int r = launch_fused(h, ab)) return r;
+    if (int r = masked_lube_post(h, a)) return r;
+    if (h->n_shared_cls > 0) {
+      const int threads = 256, grid = grid_for(h->n_shared_cls, threads, h->num_sm, 4);
+      gs_op_list_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof,
+                                                             h->gs_shared_cls, h->n_shared_cls);
+      LAUNCHED();
+      CK(cudaGetLastError());
+    }
+    if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
+    LaunchArgs ai = a; ai.elem_list = h->d_int_elem; ai.nelem = h->nint;
+    if (h->nint > 0) if (int r = launch_fused(h, ai)) return r;
+    if (int r = time_mark(h)) return r;
+    if (h->nclass > 0) {
+      const int threads = 256, grid = grid_for(h->nclass, threads, h->num_sm, 8);
+      gs_op_skip_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->gs_skip,
+                                                             h->nclass);
+      LAUNCHED();
+      CK(cudaGetLastError());
+    }
+    if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
+  } else {
+    if (int r = launch_fused(h, a)) return r;
+    if (int r = masked_lube_post(h, a)) return r;
+    if (int r = time_mark(h)) return r;
+    if (int r = gs_launch(h, f0, f1, f2, 3)) return r;
+    if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
+    if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
+  }
+  return time_mark(h);
+}
+
+int b200_adv_adjoint_compute(void* handle, const void* vx, const void* vy, const void* vz,
+                             const void* vxb, const void* vyb, const void* vzb, void* fx, void* fy,
+                             void* fz) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!vx || !vy || !vz || !vxb || !vyb || !vzb || !fx || !fy || !fz)
+    return fail(B200_ERR_ARG, "adv_adjoint_compute: null pointer");
+  if (int r = check_fields({vx, vy, vz, vxb, vyb, vzb, fx, fy, fz})) return r;
+  CK(cudaSetDevice(h->device));
+  LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, nullptr, nullptr, nullptr, nullptr, nullptr, fx, fy,
+                           fz, nullptr, nullptr, h->nelv);
+  a.fin[0] = (const double*)fx; a.fin[1] = (const double*)fy; a.fin[2] = (const double*)fz;
+  return launch_fused(h, a);
+}
+
+int b200_adv_linear_compute(void*, const void*, const void*, const void*, const void*, const void*,
+                            const void*, const void*, void*, void*, void*) {
+  return fail(B200_ERR_STATE, "compute_linear is a SURVEY.md 8(f) 'next' row; not built yet");
+}
+
+// ---- un-fused point-wise drop-ins -------------------------------------------------------------
+static int dev_sm_count() {
+  static int sm = 0;
+  if (!sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    if (sm <= 0) sm = 148;
+  }
+  return sm;
+}
+
+int b200_brinkman_compute(void* fu, void* fv, void* fw, const void* u, const void* v, const void* w,
+                          const void* chi, const int* n, void* stream) {
+  if (!fu || !fv || !fw || !u || !v || !w || !chi || !n) return fail(B200_ERR_ARG, "brinkman: null argument");
+  const int threads = 256;
+  if (aligned16(fu) && aligned16(fv) && aligned16(fw) && aligned16(u) && aligned16(v) && aligned16(w) &&
+      aligned16(chi)) {
+    brinkman_kernel<<<grid_for((*n + 1) / 2, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+        (double*)fu, (double*)fv, (double*)fw, (const double*)u, (const double*)v, (const double*)w,
+        (const double*)chi, *n);
+  } else {
+    // -1*chi*u == lube kernel with K = -1 (scalar path for unaligned views)
+    lube_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+        (double*)fu, (double*)fv, (double*)fw, (const double*)u, (const double*)v, (const double*)w,
+        (const double*)chi, -1.0, *n);
+  }
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_lube_compute(void* fu, void* fv, void* fw, const void* u, const void* v, const void* w,
+                      const void* chi, const double* K, const void* mask_d, const int* mask_size,
+                      const int* n, void* stream) {
+  if (!fu || !fv || !fw || !u || !v || !w || !chi || !K || !n) return fail(B200_ERR_ARG, "lube: null argument");
+  const int threads = 256;
+  const int ms = (mask_d && mask_size) ? *mask_size : 0;
+  if (ms > 0)
+    lube_mask_kernel<<<grid_for(ms, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+        (double*)fu, (double*)fv, (double*)fw, (const double*)u, (const double*)v, (const double*)w,
+        (const double*)chi, *K, (const int*)mask_d, ms);
+  else
+    lube_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+        (double*)fu, (double*)fv, (double*)fw, (const double*)u, (const double*)v, (const double*)w,
+        (const double*)chi, *K, *n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_opcolv(void* fx, void* fy, void* fz, const void* B, const int* n, void* stream) {
+  if (!fx || !fy || !fz || !B || !n) return fail(B200_ERR_ARG, "opcolv: null argument");
+  const int threads = 256;
+  opcolv_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+      (double*)fx, (double*)fy, (double*)fz, (const double*)B, *n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_ramp_forward(void* chi, const void* rho, const int* n, const double* f_min, const double* f_max,
+                      const double* q, const int* convex_up, void* stream) {
+  if (!chi || !rho || !n || !f_min || !f_max || !q || !convex_up) return fail(B200_ERR_ARG, "ramp: null argument");
+  const int threads = 256;
+  ramp_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+      (double*)chi, (const double*)rho, *n, *f_min, *f_max, *q, *convex_up);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_ramp_backward(void* dF_drho, const void* dF_dchi, const void* rho, const int* n,
+                       const double* f_min, const double* f_max, const double* q, const int* convex_up,
+                       void* stream) {
+  if (!dF_drho || !dF_dchi || !rho || !n || !f_min || !f_max || !q || !convex_up)
+    return fail(B200_ERR_ARG, "ramp_backward: null argument");
+  const int threads = 256;
+  ramp_backward_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+      (double*)dF_drho, (const double*)dF_dchi, (const double*)rho, *n, *f_min, *f_max, *q, *convex_up);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_sensitivity(void* sens, const void* u, const void* v, const void* w, const void* ua,
+                     const void* va, const void* wa, const double* K_obj, const int* if_lube,
+                     const int* n, void* stream) {
+  if (!sens || !u || !v || !w || !ua || !va || !wa || !K_obj || !if_lube || !n)
+    return fail(B200_ERR_ARG, "sensitivity: null argument");
+  const int threads = 256;
+  sensitivity_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+      (double*)sens, (const double*)u, (const double*)v, (const double*)w, (const double*)ua,
+      (const double*)va, (const double*)wa, *K_obj, *if_lube, *n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_steady_field_update(double* result, const void* x, void* x_old, const int* n, void* stream) {
+  if (!result || !x || !x_old || !n) return fail(B200_ERR_ARG, "steady_field_update: null argument");
+  double* d_res = nullptr;
+  CK(cudaMalloc(&d_res, sizeof(double)));
+  CK(cudaMemsetAsync(d_res, 0, sizeof(double), (cudaStream_t)stream));
+  const int threads = 256;
+  steady_update_kernel<<<grid_for(*n, threads, dev_sm_count(), 4), threads, 0, (cudaStream_t)stream>>>(
+      d_res, (const double*)x, (double*)x_old, *n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(result, d_res, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  CK(cudaFree(d_res));
+  return B200_OK;
+}
+
+// ---- gather-scatter set-up ---------------------------------------------------------------------
+int b200_gs_init(void* handle, const int64_t* key, const int* on_device) {
+  if (!handle || !key) return fail(B200_ERR_ARG, "gs_init: null argument");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  cudaStream_t st = h->stream;
+  cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep);
+  h->gs_off = h->gs_dof = h->gs_rep = nullptr;
+  h->have_gs = false;
+  if (n == 0) { h->nclass = 0; h->nmember = 0; h->have_gs = true; return B200_OK; }
+
+  int64_t *d_key_in = nullptr, *d_key = nullptr, *d_comp = nullptr, *d_comp2 = nullptr;
+  int *d_idx = nullptr, *d_dof = nullptr, *d_head = nullptr, *d_hscan = nullptr;
+  unsigned char* d_shared = nullptr;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  if (on_device && *on_device) d_key_in = const_cast<int64_t*>(key);
+  else {
+    if (int r = dmalloc(&d_key_in, n)) return r;
+    CK(cudaMemcpyAsync(d_key_in, key, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+  }
+  if (int r = dmalloc(&d_key, n)) return r;
+  if (int r = dmalloc(&d_idx, n)) return r;
+  if (int r = dmalloc(&d_dof, n)) return r;
+  const int threads = 256;
+  const int grid = grid_for(n, threads, h->num_sm, 8);
+  gs_iota_kernel<<<grid, threads, 0, st>>>(d_idx, n);
+  LAUNCHED();
+  // 1. stable radix sort of (key, dof)
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key_in, d_key, d_idx, d_dof, n, 0, 64, st));
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key_in, d_key, d_idx, d_dof, n, 0, 64, st));
+  CK(cudaFree(d_tmp)); d_tmp = nullptr;
+  if (!(on_device && *on_device)) { CK(cudaStreamSynchronize(st)); CK(cudaFree(d_key_in)); }
+  // 2. mark shared members and run heads
+  if (int r = dmalloc(&d_shared, n)) return r;
+  if (int r = dmalloc(&d_head, n)) return r;
+  if (int r = dmalloc(&d_hscan, n)) return r;
+  gs_mark_kernel<<<grid, threads, 0, st>>>(d_key, n, d_shared, d_head);
+  LAUNCHED();
+  CK(cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, d_head, d_hscan, cub::Max(), n, st));
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  CK(cub::DeviceScan::InclusiveScan(d_tmp, tmp_bytes, d_head, d_hscan, cub::Max(), n, st));
+  CK(cudaFree(d_tmp)); d_tmp = nullptr;
+  // 3. composite keys (first dof of class, dof) and rep[]
+  CK(cudaFree(d_key)); d_key = nullptr;
+  if (int r = dmalloc(&d_comp, n)) return r;
+  if (int r = dmalloc(&h->gs_rep, n)) return r;
+  gs_compose_kernel<<<grid, threads, 0, st>>>(d_dof, d_hscan, n, d_comp, h->gs_rep);
+  LAUNCHED();
+  CK(cudaFree(d_head)); CK(cudaFree(d_hscan)); CK(cudaFree(d_idx));
+  // 4. keep shared members only
+  int64_t* d_ns = nullptr;
+  if (int r = dmalloc(&d_ns, 1)) return r;
+  if (int r = dmalloc(&d_comp2, n)) return r;
+  CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_comp, d_shared, d_comp2, d_ns, n, st));
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  CK(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_comp, d_shared, d_comp2, d_ns, n, st));
+  CK(cudaFree(d_tmp)); d_tmp = nullptr;
+  int64_t ns = 0;
+  CK(cudaMemcpyAsync(&ns, d_ns, sizeof ns, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(d_shared)); CK(cudaFree(d_dof));
+  h->nmember = ns;
+  if (ns == 0) {
+    h->nclass = 0;
+    CK(cudaFree(d_comp)); CK(cudaFree(d_comp2)); CK(cudaFree(d_ns));
+    if (int r = dmalloc(&h->gs_off, 1)) return r;
+    if (int r = dmalloc(&h->gs_dof, 1)) return r;
+    h->have_gs = true;
+    return B200_OK;
+  }
+  // 5. order members by (first dof of class, dof): element-surface order
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_comp2, d_comp, ns, 0, 64, st));
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  CK(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_comp2, d_comp, ns, 0, 64, st));
+  CK(cudaFree(d_tmp)); d_tmp = nullptr;
+  CK(cudaFree(d_comp2));
+  unsigned char* d_h2 = nullptr;
+  if (int r = dmalloc(&h->gs_dof, ns)) return r;
+  if (int r = dmalloc(&d_h2, ns)) return r;
+  const int grid2 = grid_for(ns, threads, h->num_sm, 8);
+  gs_split_kernel<<<grid2, threads, 0, st>>>(d_comp, ns, h->gs_dof, d_h2);
+  LAUNCHED();
+  // 6. class offsets = positions of heads (+ terminator)
+  int* d_off_tmp = nullptr;
+  if (int r = dmalloc(&d_off_tmp, ns + 1)) return r;
+  thrust::counting_iterator<int> cnt(0);
+  CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, cnt, d_h2, d_off_tmp, d_ns, ns, st));
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  CK(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, cnt, d_h2, d_off_tmp, d_ns, ns, st));
+  CK(cudaFree(d_tmp)); d_tmp = nullptr;
+  int64_t nc = 0;
+  CK(cudaMemcpyAsync(&nc, d_ns, sizeof nc, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->nclass = (int)nc;
+  if (int r = dmalloc(&h->gs_off, nc + 1)) return r;
+  CK(cudaMemcpyAsync(h->gs_off, d_off_tmp, sizeof(int) * nc, cudaMemcpyDeviceToDevice, st));
+  const int ns_i = (int)ns;
+  CK(cudaMemcpyAsync(h->gs_off + nc, &ns_i, sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(d_off_tmp)); CK(cudaFree(d_h2)); CK(cudaFree(d_comp)); CK(cudaFree(d_ns));
+  h->have_gs = true;
+  return B200_OK;
+}
+
+int b200_gs_get_classes(void* handle, int64_t* class_id, int64_t* nclass) {
+  if (!handle || !class_id) return fail(B200_ERR_ARG, "gs_get_classes: null argument");
+  Handle* h = H(handle);
+  if (!h->have_gs) return fail(B200_ERR_STATE, "b200_gs_init not called");
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  if (n == 0) { if (nclass) *nclass = 0; return B200_OK; }
+  cudaStream_t st = h->stream;
+  int *d_isrep = nullptr, *d_scan = nullptr;
+  int64_t* d_cid = nullptr;
+  if (int r = dmalloc(&d_isrep, n)) return r;
+  if (int r = dmalloc(&d_scan, n)) return r;
+  if (int r = dmalloc(&d_cid, n)) return r;
+  const int threads = 256;
+  const int grid = grid_for(n, threads, h->num_sm, 8);
+  gs_isrep_kernel<<<grid, threads, 0, st>>>(h->gs_rep, n, d_isrep);
+  LAUNCHED();
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_isrep, d_scan, n, st));
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  CK(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_isrep, d_scan, n, st));
+  gs_classid_kernel<<<grid, threads, 0, st>>>(h->gs_rep, d_scan, n, d_cid);
+  LAUNCHED();
+  CK(cudaMemcpyAsync(class_id, d_cid, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+  int last_scan = 0, last_rep = 0;
+  CK(cudaMemcpyAsync(&last_scan, d_scan + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&last_rep, d_isrep + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (nclass) *nclass = (int64_t)last_scan + last_rep;
+  CK(cudaFree(d_tmp)); CK(cudaFree(d_isrep)); CK(cudaFree(d_scan)); CK(cudaFree(d_cid));
+  return B200_OK;
+}
+
+int b200_gs_op(void* handle, void* f) {
+  if (!handle || !f) return fail(B200_ERR_ARG, "gs_op: null argument");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  double* f0 = (double*)f;
+  if (int r = gs_launch(h, f0, f0, f0, 1)) return r;
+  if (int r = gs_exchange(h, f0, f0, f0, 1)) return r;
+  return gs_finish_exchange(h, f0, f0, f0, 1);
+}
+
+int b200_gs_op3(void* handle, void* fx, void* fy, void* fz) {
+  if (!handle || !fx || !fy || !fz) return fail(B200_ERR_ARG, "gs_op3: null argument");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  double *f0 = (double*)fx, *f1 = (double*)fy, *f2 = (double*)fz;
+  if (int r = gs_launch(h, f0, f1, f2, 3)) return r;
+  if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
+  return gs_finish_exchange(h, f0, f1, f2, 3);
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------
+int b200_comm_unique_id(char* id128) {
+  if (!id128) return fail(B200_ERR_ARG, "comm_unique_id: null argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NK(ncclGetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return B200_OK;
+}
+
+int b200_comm_init(void* handle, const char* id128, const int* rank, const int* nranks) {
+  if (!handle || !id128 || !rank || !nranks) return fail(B200_ERR_ARG, "comm_init: null argument");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NK(ncclCommInitRank(&h->comm, *nranks, id, *rank));
+  h->rank = *rank; h->nranks = *nranks;
+  CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_recv, cudaEventDisableTiming));
+  return B200_OK;
+}
+
+int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof, const int* nneigh,
+                        const int* neigh_rank, const int* neigh_off, const int* neigh_idx) {
+  if (!handle || !nshared || !nneigh) return fail(B200_ERR_ARG, "gs_init_shared: null argument");
+  Handle* h = H(handle);
+  if (!h->have_gs) return fail(B200_ERR_STATE, "gs_init_shared: call b200_gs_init first");
+  CK(cudaSetDevice(h->device));
+  const int ns = *nshared, nn = *nneigh;
+  h->nshared = ns; h->nneigh = nn;
+  cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
+  cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->gs_skip);
+  cudaFree(h->gs_shared_cls);
+  h->d_send_dof = h->d_shared_dof = h->d_s_class = h->d_c_off = h->d_c_src = nullptr;
+  h->d_send = h->d_recv = nullptr; h->gs_skip = nullptr; h->gs_shared_cls = nullptr;
+  h->n_shared_cls = 0; h->nsend = 0;
+  if (ns == 0 || nn == 0) { h->nshared = 0; return B200_OK; }
+  if (!shared_dof || !neigh_rank || !neigh_off || !neigh_idx) return fail(B200_ERR_ARG, "gs_init_shared: null list");
+  // neighbours in ascending rank order so that every rank sums contributions in the same order
+  std::vector<int> order(nn);
+  for (int j = 0; j < nn; j++) order[j] = j;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return neigh_rank[a] < neigh_rank[b]; });
+  h->neigh_rank.assign(nn, 0);
+  h->neigh_off.assign(nn + 1, 0);
+  std::vector<int> send_dof;
+  std::vector<std::vector<std::pair<int, int>>> contrib(ns);   // (rank, src)
+  for (int s = 0; s < ns; s++) contrib[s].push_back({h->rank, -1});
+  for (int jj = 0; jj < nn; jj++) {
+    const int j = order[jj];
+    h->neigh_rank[jj] = neigh_rank[j];
+    if (neigh_rank[j] == h->rank) return fail(B200_ERR_ARG, "gs_init_shared: neighbour == own rank");
+    for (int i = neigh_off[j]; i < neigh_off[j + 1]; i++) {
+      const int s = neigh_idx[i];
+      if (s < 0 || s >= ns) return fail(B200_ERR_ARG, "gs_init_shared: neigh_idx out of range");
+      contrib[s].push_back({neigh_rank[j], (int)send_dof.size()});
+      send_dof.push_back(shared_dof[s]);
+    }
+    h->neigh_off[jj + 1] = (int)send_dof.size();
+  }
+  h->nsend = (int)send_dof.size();
+  std::vector<int> c_off(ns + 1, 0), c_src;
+  for (int s = 0; s < ns; s++) {
+    std::sort(contrib[s].begin(), contrib[s].end());
+    for (auto& pr : contrib[s]) c_src.push_back(pr.second);
+    c_off[s + 1] = (int)c_src.size();
+  }
+  if (int r = dmalloc(&h->d_send_dof, send_dof.size())) return r;
+  if (int r = dmalloc(&h->d_shared_dof, ns)) return r;
+  if (int r = dmalloc(&h->d_s_class, ns)) return r;
+  if (int r = dmalloc(&h->d_c_off, ns + 1)) return r;
+  if (int r = dmalloc(&h->d_c_src, c_src.size())) return r;
+  if (int r = dmalloc(&h->d_send, (size_t)h->nsend * 3)) return r;
+  if (int r = dmalloc(&h->d_recv, (size_t)h->nsend * 3)) return r;
+  CK(cudaMemcpy(h->d_send_dof, send_dof.data(), sizeof(int) * send_dof.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_shared_dof, shared_dof, sizeof(int) * ns, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_c_off, c_off.data(), sizeof(int) * (ns + 1), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_c_src, c_src.data(), sizeof(int) * c_src.size(), cudaMemcpyHostToDevice));
+  // local class of every shared node (-1: the node has a single local member)
+  if (int r = dmalloc(&h->gs_skip, (size_t)std::max(h->nclass, 1))) return r;
+  CK(cudaMemsetAsync(h->gs_skip, 0, (size_t)std::max(h->nclass, 1), h->stream));
+  const int threads = 256;
+  gs_find_class_kernel<<<grid_for(ns, threads, h->num_sm, 4), threads, 0, h->stream>>>(
+      h->d_shared_dof, ns, h->gs_rep, h->gs_off, h->gs_dof, h->nclass, h->d_s_class, h->gs_skip);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  // compact list of local classes that hold a shared node
+  std::vector<int> s_class(ns);
+  CK(cudaMemcpyAsync(s_class.data(), h->d_s_class, sizeof(int) * ns, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<int> cls;
+  for (int s = 0; s < ns; s++) if (s_class[s] >= 0) cls.push_back(s_class[s]);
+  std::sort(cls.begin(), cls.end());
+  cls.erase(std::unique(cls.begin(), cls.end()), cls.end());
+  h->n_shared_cls = (int)cls.size();
+  if (int r = dmalloc(&h->gs_shared_cls, cls.size())) return r;
+  if (!cls.empty())
+    CK(cudaMemcpy(h->gs_shared_cls, cls.data(), sizeof(int) * cls.size(), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* bnd_elem) {
+  if (!handle || !nbnd) return fail(B200_ERR_ARG, "set_boundary_elements: null argument");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  cudaFree(h->d_bnd_elem); cudaFree(h->d_int_elem);
+  h->d_bnd_elem = h->d_int_elem = nullptr;
+  h->nbnd = *nbnd; h->nint = 0;
+  if (*nbnd == 0) return B200_OK;
+  if (!bnd_elem) return fail(B200_ERR_ARG, "set_boundary_elements: null list");
+  std::vector<char> isb(h->nelv, 0);
+  for (int i = 0; i < *nbnd; i++) {
+    if (bnd_elem[i] < 0 || bnd_elem[i] >= h->nelv) return fail(B200_ERR_ARG, "boundary element out of range");
+    isb[bnd_elem[i]] = 1;
+  }
+  std::vector<int> bnd, inte;
+  for (int e = 0; e < h->nelv; e++) (isb[e] ? bnd : inte).push_back(e);
+  h->nbnd = (int)bnd.size(); h->nint = (int)inte.size();
+  if (int r = dmalloc(&h->d_bnd_elem, bnd.size())) return r;
+  if (int r = dmalloc(&h->d_int_elem, inte.size())) return r;
+  CK(cudaMemcpy(h->d_bnd_elem, bnd.data(), sizeof(int) * bnd.size(), cudaMemcpyHostToDevice));
+  if (!inte.empty()) CK(cudaMemcpy(h->d_int_elem, inte.data(), sizeof(int) * inte.size(), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+// ---- host-staged step (bench.py "e2e") ----------------------------------------------------------
+int b200_adjrhs_step_host(void* handle, const double* vx, const double* vy, const double* vz,
+                          const double* vxb, const double* vyb, const double* vzb, const double* rho,
+                          double* fx, double* fy, double* fz, double* sens) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!vx || !vy || !vz || !vxb || !vyb || !vzb || !rho || !fx || !fy || !fz)
+    return fail(B200_ERR_ARG, "step_host: null argument");
+  if (!h->have_gs) return fail(B200_ERR_STATE, "step_host: b200_gs_init not called");
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  const int64_t N = (int64_t)h->lx * h->lx * h->lx;
+  if (!h->stage[0]) {
+    for (int i = 0; i < 11; i++) if (int r = dmalloc(&h->stage[i], n)) return r;
+    CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  }
+  const double* in[7] = {vx, vy, vz, vxb, vyb, vzb, rho};
+  double** st = h->stage;   // 0..6 inputs, 7..9 f, 10 sens
+  // element chunks: copy chunk c+1 while chunk c computes; sens goes back as soon as its chunk is done
+  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(16, h->nelv / 1024));
+  while ((int)h->ev_h2d.size() < nchunk) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_h2d.push_back(a); h->ev_k.push_back(b);
+  }
+  // the caller's stream must be idle with respect to the staging buffers
+  CK(cudaEventRecord(h->ev_done, h->stream));
+  CK(cudaStreamWaitEvent(h->h2d_stream, h->ev_done, 0));
+  CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done, 0));
+  for (int c = 0; c < nchunk; c++) {
+    const int e0 = (int)((int64_t)h->nelv * c / nchunk), e1 = (int)((int64_t)h->nelv * (c + 1) / nchunk);
+    const size_t o = (size_t)e0 * N, cnt = (size_t)(e1 - e0) * N;
+    for (int i = 0; i < 7; i++)
+      CK(cudaMemcpyAsync(st[i] + o, in[i] + o, cnt * 8, cudaMemcpyHostToDevice, h->h2d_stream));
+    CK(cudaEventRecord(h->ev_h2d[c], h->h2d_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[c], 0));
+    LaunchArgs a = make_args(st[0], st[1], st[2], st[3], st[4], st[5], st[6], nullptr, nullptr, nullptr,
+                             nullptr, st[7], st[8], st[9], sens ? st[10] : nullptr, nullptr, e1 - e0);
+    a.elem_begin = e0;
+    if (int r = launch_fused(h, a)) return r;
+    if (sens) {
+      CK(cudaEventRecord(h->ev_k[c], h->stream));
+      CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_k[c], 0));
+      CK(cudaMemcpyAsync(sens + o, st[10] + o, cnt * 8, cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
+  }
+  {
+    LaunchArgs a = make_args(st[0], st[1], st[2], st[3], st[4], st[5], st[6], nullptr, nullptr, nullptr,
+                             nullptr, st[7], st[8], st[9], nullptr, nullptr, h->nelv);
+    if (int r = masked_lube_post(h, a)) return r;
+  }
+  if (int r = gs_launch(h, st[7], st[8], st[9], 3)) return r;
+  if (int r = gs_exchange(h, st[7], st[8], st[9], 3)) return r;
+  if (int r = gs_finish_exchange(h, st[7], st[8], st[9], 3)) return r;
+  double* out[3] = {fx, fy, fz};
+  for (int i = 0; i < 3; i++)
+    CK(cudaMemcpyAsync(out[i], st[7 + i], n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->d2h_stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200_OK;
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------------
+int b200_adjrhs_enable_timing(void* handle, const int* flag) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  h->timing = flag && *flag;
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  h->tev.clear();
+  return B200_OK;
+}
+
+int b200_adjrhs_get_timing(void* handle, double* elem_kernel_ms, double* gs_ms, int64_t* launches) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  double a = 0.0, b = 0.0;
+  const size_t nt = h->tev.size() / 3;
+  for (size_t i = 0; i < nt; i++) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->tev[3 * i], h->tev[3 * i + 1])); a += ms;
+    CK(cudaEventElapsedTime(&ms, h->tev[3 * i + 1], h->tev[3 * i + 2])); b += ms;
+  }
+  if (elem_kernel_ms) *elem_kernel_ms = nt ? a / nt : 0.0;
+  if (gs_ms) *gs_ms = nt ? b / nt : 0.0;
+  if (launches) *launches = (int64_t)nt;
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// Un-fused point-wise drop-ins, one per reference plug-in method (include/neko_top_b200.h).
+// Pure streaming kernels: 128-bit coalesced loads/stores, grid sized as a multiple of the SM count,
+// grid-stride loops.  Citations relative to /root/reference/sources.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+__device__ __forceinline__ double2 ld2(const double* p, int64_t i) {
+  return *reinterpret_cast<const double2*>(p + i);
+}
+__device__ __forceinline__ void st2(double* p, int64_t i, double2 v) {
+  *reinterpret_cast<double2*>(p + i) = v;
+}
+
+// simple_brinkman_source_term.f90:149-151  field_subcol3(f, u, chi): f = f - u*chi
+__global__ void brinkman_kernel(double* __restrict__ fu, double* __restrict__ fv, double* __restrict__ fw,
+                                const double* __restrict__ u, const double* __restrict__ v,
+                                const double* __restrict__ w, const double* __restrict__ chi, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  for (; i + 1 < n; i += stride) {
+    const double2 c = ld2(chi, i);
+    double2 a = ld2(fu, i), b = ld2(u, i);
+    a.x -= b.x * c.x; a.y -= b.y * c.y; st2(fu, i, a);
+    a = ld2(fv, i); b = ld2(v, i);
+    a.x -= b.x * c.x; a.y -= b.y * c.y; st2(fv, i, a);
+    a = ld2(fw, i); b = ld2(w, i);
+    a.x -= b.x * c.x; a.y -= b.y * c.y; st2(fw, i, a);
+  }
+  if (i < n) {  // odd tail
+    fu[i] -= u[i] * chi[i]; fv[i] -= v[i] * chi[i]; fw[i] -= w[i] * chi[i];
+  }
+}
+
+// adjoint_lube_source_term.f90:189-203  f_i += u_i*(chi*K), everywhere
+__global__ void lube_kernel(double* __restrict__ fu, double* __restrict__ fv, double* __restrict__ fw,
+                            const double* __restrict__ u, const double* __restrict__ v,
+                            const double* __restrict__ w, const double* __restrict__ chi, double K,
+                            int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double c = chi[i] * K;
+    fu[i] += u[i] * c; fv[i] += v[i] * c; fw[i] += w[i] * c;
+  }
+}
+// same, restricted to a point zone: mask holds 1-based indices (mask_ops.f90:55-82 zeroes the rest)
+__global__ void lube_mask_kernel(double* __restrict__ fu, double* __restrict__ fv, double* __restrict__ fw,
+                                 const double* __restrict__ u, const double* __restrict__ v,
+                                 const double* __restrict__ w, const double* __restrict__ chi, double K,
+                                 const int* __restrict__ mask, int mask_size) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < mask_size; m += stride) {
+    const int64_t i = (int64_t)mask[m] - 1;
+    const double c = chi[i] * K;
+    fu[i] += u[i] * c; fv[i] += v[i] * c; fw[i] += w[i] * c;
+  }
+}
+// masked lube contribution added after the fused kernel: f_i += B*(K*RAMP(rho))*vb_i on the mask
+__global__ void lube_mask_post_kernel(double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                                      const double* __restrict__ ub, const double* __restrict__ vb,
+                                      const double* __restrict__ wb, const double* __restrict__ rho_or_chi,
+                                      const double* __restrict__ B, double K, int do_ramp, int convex_up,
+                                      double f_min, double f_max, double q,
+                                      const int* __restrict__ mask, int mask_size) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < mask_size; m += stride) {
+    const int64_t i = (int64_t)mask[m] - 1;
+    double chi = rho_or_chi[i];
+    if (do_ramp) {
+      if (convex_up) chi = f_min + (f_max - f_min) * chi * (1.0 + q) / (chi + q);
+      else chi = f_min + (f_max - f_min) * chi / (1.0 + q * (1.0 - chi));
+    }
+    const double c = (chi * K) * B[i];
+    fx[i] += ub[i] * c; fy[i] += vb[i] * c; fz[i] += wb[i] * c;
+  }
+}
+
+// adjoint_pnpn.f90:672-676 opcolv
+__global__ void opcolv_kernel(double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                              const double* __restrict__ B, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double b = B[i];
+    fx[i] *= b; fy[i] *= b; fz[i] *= b;
+  }
+}
+
+// RAMP_mapping.f90:182-196 / 227-241
+__global__ void ramp_kernel(double* __restrict__ chi, const double* __restrict__ rho, int64_t n, double f_min,
+                            double f_max, double q, int convex_up) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double r = rho[i];
+    chi[i] = convex_up ? f_min + (f_max - f_min) * r * (1.0 + q) / (r + q)
+                       : f_min + (f_max - f_min) * r / (1.0 + q * (1.0 - r));
+  }
+}
+// RAMP_mapping.f90:203-222 / 248-267
+__global__ void ramp_backward_kernel(double* __restrict__ out, const double* __restrict__ dF,
+                                     const double* __restrict__ rho, int64_t n, double f_min, double f_max,
+                                     double q, int convex_up) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double r = rho[i];
+    if (convex_up) {
+      out[i] = (f_max - f_min) * (q + 1.0) / ((r + q) * (r + q)) * dF[i];
+    } else {
+      const double d = 1.0 - q * (r - 1.0);
+      out[i] = (f_max - f_min) * (q + 1.0) / (d * d) * dF[i];
+    }
+  }
+}
+
+// minimum_dissipation_objective_function.f90:260-301
+__global__ void sensitivity_kernel(double* __restrict__ S, const double* __restrict__ u,
+                                   const double* __restrict__ v, const double* __restrict__ w,
+                                   const double* __restrict__ ua, const double* __restrict__ va,
+                                   const double* __restrict__ wa, double K, int if_lube, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double s = u[i] * ua[i];
+    s += v[i] * va[i];
+    s += w[i] * wa[i];
+    s *= -1.0;
+    if (if_lube) {
+      double l = u[i] * u[i];
+      l += v[i] * v[i];
+      l += w[i] * w[i];
+      s += K * l;
+    }
+    S[i] = s;
+  }
+}
+
+// steady_simcomp.f90:158-176: d = old - new; acc += d*d; old = new.  One double atomic per CTA.
+__global__ void steady_update_kernel(double* __restrict__ result, const double* __restrict__ x,
+                                     double* __restrict__ x_old, int64_t n) {
+  __shared__ double red[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double xn = x[i];
+    const double d = x_old[i] - xn;
+    acc = fma(d, d, acc);
+    x_old[i] = xn;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) atomicAdd(result, acc);
+  }
+}
+
+}  // namespace b200

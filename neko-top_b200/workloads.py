@@ -1,0 +1,215 @@
+"""Synthetic meshes and fields for BASELINE.json's configs.
+
+Everything is generated from the GLOBAL node lattice, so fields are C0 across elements and across
+GPU partitions, and any rank can generate exactly its own brick.  torch is the array library (CUDA
+in bench.py, CPU in the tests); nothing here is inside a timed region.
+
+Element order inside a brick: e = ex + nex*(ey + ney*ez) (x fastest); points (k, j, i) with i fastest,
+i.e. tensors of shape (nelv, lx, lx, lx) are the Fortran arrays x(lx,lx,lx,nelv).
+"""
+from dataclasses import dataclass, field
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import sem
+
+
+@dataclass
+class BoxBrick:
+    """One rank's brick of a structured box mesh of hexahedra."""
+    lx: int
+    ne: Tuple[int, int, int]                       # local elements (nex, ney, nez)
+    ne_global: Tuple[int, int, int] = None         # global elements (defaults to ne)
+    offset: Tuple[int, int, int] = (0, 0, 0)       # brick origin in the global element lattice
+    origin: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    length: Tuple[float, float, float] = (1.0, 1.0, 1.0)   # global box size
+    deform: float = 0.0                            # amplitude of a smooth non-affine warp
+    name: str = "box"
+
+    def __post_init__(self):
+        if self.ne_global is None:
+            self.ne_global = tuple(self.ne)
+
+    @property
+    def nelv(self):
+        return self.ne[0] * self.ne[1] * self.ne[2]
+
+    @property
+    def n(self):
+        return self.nelv * self.lx ** 3
+
+
+# ---- BASELINE.json configs ---------------------------------------------------------------------
+def config_duct(lx):
+    """configs[0] (lx=6) / configs[2] (lx=8): duct 24x8x8 on [0,10]x[-.5,.5]^2
+    (/root/reference/data/thermal_mix_channel/square_pipe.jou:6-14)."""
+    return BoxBrick(lx=lx, ne=(24, 8, 8), origin=(0.0, -0.5, -0.5), length=(10.0, 1.0, 1.0), name="duct24x8x8")
+
+
+def config_box(ne, lx=8, deform=0.0):
+    """configs[1]: uniform box [0,1]^3 of ne^3 hexes."""
+    return BoxBrick(lx=lx, ne=(ne, ne, ne), deform=deform, name=f"box{ne}^3")
+
+
+def rank_grid(nranks):
+    """configs[3]: GPU grids 1, 2x1x1, 2x2x1, 2x2x2."""
+    grids = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+    if nranks not in grids:
+        raise ValueError(f"rank grid for {nranks} ranks not defined (1, 2, 4, 8)")
+    return grids[nranks]
+
+
+def config_weak(rank, nranks, ne_per_gpu=64, lx=8):
+    """configs[3]: ne_per_gpu^3 elements per GPU, global box (ne*px) x (ne*py) x (ne*pz)."""
+    px, py, pz = rank_grid(nranks)
+    rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
+    ne = (ne_per_gpu,) * 3
+    return BoxBrick(lx=lx, ne=ne, ne_global=(ne_per_gpu * px, ne_per_gpu * py, ne_per_gpu * pz),
+                    offset=(rx * ne_per_gpu, ry * ne_per_gpu, rz * ne_per_gpu),
+                    length=(float(px), float(py), float(pz)), name=f"box{ne_per_gpu}^3/gpu")
+
+
+def config_sweep(lx, target_dof=1.0e8):
+    """configs[4]: E = round(1e8/lx^3) arranged as a near-cubic box."""
+    ne = max(1, round((target_dof / lx ** 3) ** (1.0 / 3.0)))
+    return BoxBrick(lx=lx, ne=(ne, ne, ne), name=f"sweep lx={lx} box{ne}^3")
+
+
+# ---- lattice indices, coordinates, keys ------------------------------------------------------------
+def _lattice(brick, device):
+    """Global lattice index (gi, gj, gk) of every local point, each (nelv, lx, lx, lx) int64."""
+    lx = brick.lx
+    nex, ney, nez = brick.ne
+    e = torch.arange(brick.nelv, device=device, dtype=torch.int64)
+    ex = (e % nex) + brick.offset[0]
+    ey = ((e // nex) % ney) + brick.offset[1]
+    ez = (e // (nex * ney)) + brick.offset[2]
+    p = torch.arange(lx, device=device, dtype=torch.int64)
+    gi = (ex * (lx - 1)).view(-1, 1, 1, 1) + p.view(1, 1, 1, lx)
+    gj = (ey * (lx - 1)).view(-1, 1, 1, 1) + p.view(1, 1, lx, 1)
+    gk = (ez * (lx - 1)).view(-1, 1, 1, 1) + p.view(1, lx, 1, 1)
+    shape = (brick.nelv, lx, lx, lx)
+    return gi.expand(shape), gj.expand(shape), gk.expand(shape)
+
+
+def node_keys(brick, device="cpu"):
+    """int64 global node id of every local dof: two dofs are the same physical GLL node iff their
+    keys are equal."""
+    lx = brick.lx
+    gi, gj, gk = _lattice(brick, device)
+    NXg = brick.ne_global[0] * (lx - 1) + 1
+    NYg = brick.ne_global[1] * (lx - 1) + 1
+    return (gi + NXg * (gj + NYg * gk)).contiguous()
+
+
+def coords(brick, device="cpu"):
+    """Nodal coordinates x, y, z (nelv, lx, lx, lx) float64; shared nodes get bit-identical values."""
+    lx = brick.lx
+    zg, _ = sem.zwgll(lx)
+    t = torch.as_tensor((zg + 1.0) * 0.5, dtype=torch.float64, device=device)   # 0 .. 1 exactly at ends
+    nex, ney, nez = brick.ne
+    e = torch.arange(brick.nelv, device=device, dtype=torch.int64)
+    ex = ((e % nex) + brick.offset[0]).to(torch.float64).view(-1, 1, 1, 1)
+    ey = (((e // nex) % ney) + brick.offset[1]).to(torch.float64).view(-1, 1, 1, 1)
+    ez = ((e // (nex * ney)) + brick.offset[2]).to(torch.float64).view(-1, 1, 1, 1)
+    shape = (brick.nelv, lx, lx, lx)
+    # normalised global coordinates in [0,1]
+    X = ((ex + t.view(1, 1, 1, lx)) / brick.ne_global[0]).expand(shape)
+    Y = ((ey + t.view(1, 1, lx, 1)) / brick.ne_global[1]).expand(shape)
+    Z = ((ez + t.view(1, lx, 1, 1)) / brick.ne_global[2]).expand(shape)
+    if brick.deform != 0.0:
+        a = brick.deform
+        two_pi = 2.0 * np.pi
+        s = torch.sin(two_pi * X) * torch.sin(two_pi * Y) * torch.sin(two_pi * Z)
+        X, Y, Z = X + a * s, Y + 0.7 * a * s, Z - 0.5 * a * s
+    x = brick.origin[0] + brick.length[0] * X
+    y = brick.origin[1] + brick.length[1] * Y
+    z = brick.origin[2] + brick.length[2] * Z
+    return x.contiguous(), y.contiguous(), z.contiguous()
+
+
+# ---- deterministic node-keyed pseudo-random numbers (splitmix64) ---------------------------------------
+def _i64(v):
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+_GAMMA, _M1, _M2 = _i64(0x9E3779B97F4A7C15), _i64(0xBF58476D1CE4E5B9), _i64(0x94D049BB133111EB)
+
+
+def _lsr(x, s):
+    """logical shift right on two's-complement int64 tensors"""
+    return (x >> s) & ((1 << (64 - s)) - 1)
+
+
+def hash_uniform(keys, seed):
+    """U[0,1) per key, identical on every device/rank (wrap-around int64 arithmetic)."""
+    z = keys * _GAMMA + _i64(seed * 0x2545F4914F6CDD1D + 0x1234567)
+    z = (z ^ _lsr(z, 30)) * _M1
+    z = (z ^ _lsr(z, 27)) * _M2
+    z = z ^ _lsr(z, 31)
+    return _lsr(z, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
+
+
+def hash_uniform_numpy(keys, seed):
+    """numpy twin of hash_uniform (uint64 arithmetic) -- used by the tests to pin the generator."""
+    k = np.asarray(keys).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        z = k * np.uint64(0x9E3779B97F4A7C15) + np.uint64((seed * 0x2545F4914F6CDD1D + 0x1234567) & ((1 << 64) - 1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+@dataclass
+class Fields:
+    ub: list          # base flow U_b (3)
+    v: list           # adjoint velocity u-dagger (3)
+    rho: torch.Tensor  # filtered design rho-tilde in [0,1]
+
+
+def make_fields(brick, x, y, z, keys):
+    """configs[1] recipe: rho ~ U(0,1) per global node (seed 1234); smooth analytic base flow; adjoint
+    velocity = smooth part + 1e-2 * node-keyed noise (seed 4321)."""
+    X = (x - brick.origin[0]) / brick.length[0]
+    Y = (y - brick.origin[1]) / brick.length[1]
+    Z = (z - brick.origin[2]) / brick.length[2]
+    pi = np.pi
+    r = torch.sqrt(X * X + Y * Y + Z * Z)
+    amp = 1.0 + 0.1 * r
+    ub = [torch.sin(pi * X) * torch.cos(pi * Y) * torch.cos(pi * Z) * amp,
+          -torch.cos(pi * X) * torch.sin(pi * Y) * torch.cos(pi * Z) * amp,
+          0.3 * torch.sin(pi * X) * torch.sin(pi * Y) * torch.cos(pi * Z) * amp]
+    v = [torch.cos(2 * pi * X) * torch.sin(pi * Y) + 0.5 * Z + 1e-2 * (hash_uniform(keys, 4321) - 0.5),
+         torch.sin(pi * X) * torch.cos(2 * pi * Z) - 0.25 * Y + 1e-2 * (hash_uniform(keys, 4322) - 0.5),
+         torch.cos(pi * Y) * torch.sin(2 * pi * X) + 0.1 * X * Z + 1e-2 * (hash_uniform(keys, 4323) - 0.5)]
+    rho = hash_uniform(keys, 1234)
+    return Fields([a.contiguous() for a in ub], [a.contiguous() for a in v], rho.contiguous())
+
+
+def brinkman_zone_chi(x, y, z, box=((4.75, 5.25), (-0.5, 0.5), (-0.5, 0.0)), perm=1000.0):
+    """configs[0]/[2]: chi = 1000 inside the `lowperm` box, 0 elsewhere
+    (/root/reference/examples/permeability_block/permeability_3.case:73-90)."""
+    inside = ((x >= box[0][0]) & (x <= box[0][1]) & (y >= box[1][0]) & (y <= box[1][1])
+              & (z >= box[2][0]) & (z <= box[2][1]))
+    return torch.where(inside, torch.full_like(x, perm), torch.zeros_like(x))
+
+
+def interface_candidates(brick, device="cpu"):
+    """Bool mask (nelv, lx, lx, lx): dofs on a brick face that is an interior face of the global box,
+    i.e. the only dofs that can be shared with another rank."""
+    lx = brick.lx
+    gi, gj, gk = _lattice(brick, device)
+    m = torch.zeros((brick.nelv, lx, lx, lx), dtype=torch.bool, device=device)
+    for g, d in ((gi, 0), (gj, 1), (gk, 2)):
+        lo = brick.offset[d] * (lx - 1)
+        hi = (brick.offset[d] + brick.ne[d]) * (lx - 1)
+        gmax = brick.ne_global[d] * (lx - 1)
+        if lo > 0:
+            m |= (g == lo)
+        if hi < gmax:
+            m |= (g == hi)
+    return m

@@ -1,0 +1,136 @@
+/*
+ * oracle.h -- CPU restatement (plain C, fp64) of Neko-TOP's adjoint-RHS hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
+ * and only as the checker / the timed CPU baseline.  The product path (neko-top_b200/) never
+ * calls into this library and has no CPU fallback.
+ *
+ * PARITY UNPINNED: the reference tree holds no golden vector, known-answer test or fixture for
+ * this path, and the reference cannot be built here (no Fortran, no
+ * MPI, Neko itself is an un-vendored, unpinned `develop` dependency: scripts/dependencies.sh:181-187).
+ * The oracle is therefore anchored on (i) the reference's own call sites, restated line by line
+ * below, (ii) the published Nek5000/Neko operator definitions (opgrad, cdtp, conv1, tnsr3d,
+ * speclib zwgll/zwgl/dgll) and (iii) mathematical identities checked in tests/ (polynomial
+ * exactness, discrete adjoint identity <v, L u> = <L^T v, u>).
+ *
+ * Memory layout everywhere: Fortran column-major x(lx,lx,lx,nelv), i fastest, element slowest.
+ * All citations are relative to /root/reference.
+ */
+#ifndef NEKOTOP_ORACLE_H
+#define NEKOTOP_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- speclib restatements (Neko math/speclib.f90 = Nek5000 speclib; not vendored) ---------- */
+void orc_zwgll(double *z, double *w, int np);              /* Gauss-Lobatto-Legendre nodes+weights */
+void orc_zwgl(double *z, double *w, int np);               /* Gauss-Legendre nodes+weights        */
+void orc_dgll(double *D, const double *z, int np);         /* D(i,j) col-major: D[i + np*j]       */
+void orc_deriv_matrix(double *D, const double *z, int np); /* Lagrange derivative on any nodes    */
+void orc_interp_matrix(double *J, const double *zto, int nto, const double *zfrom, int nfrom);
+                                                           /* J(a,m) col-major: J[a + nto*m]      */
+
+/* ---- coef_t restatement: geometric factors from nodal coordinates (Neko sem/coef.f90) -------
+ * G[0..8] = drdx,dsdx,dtdx, drdy,dsdy,dtdy, drdz,dsdz,dtdz  (cofactors, NOT divided by jac),
+ * jac, B = jac*w3.  SURVEY.md 8c lists the formulas. */
+void orc_geom(int lx, int nelv, const double *D, const double *w,
+              const double *x, const double *y, const double *z,
+              double *G[9], double *jac, double *B);
+
+/* ---- Neko operators the path calls ------------------------------------------ */
+/* tensor-product interpolation v = (A x A x A) u, A is (nv x nu) col-major; per element */
+void orc_tnsr3d(double *v, int nv, const double *u, int nu, const double *A, int nelv);
+/* transpose map: u = (A^T x A^T x A^T) v (interpolator_t%map to the coarse space) */
+void orc_tnsr3d_t(double *u, int nu, const double *v, int nv, const double *A, int nelv);
+void orc_opgrad(double *ux, double *uy, double *uz, const double *u, int lx, int nelv,
+                const double *D, const double *w3, double *const G[9]);
+void orc_cdtp(double *dtx, const double *x, const double *dr, const double *ds, const double *dt,
+              int lx, int nelv, const double *D, const double *w3);
+void orc_conv1(double *du, const double *u, const double *vx, const double *vy, const double *vz,
+               int lx, int nelv, const double *D, double *const G[9], const double *jacinv);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* adv_adjoint_no_dealias.f90:119-255 (intended = device-branch semantics :162-201,269-303).
+ * f is IN/OUT (accumulated).  bug_compat!=0 reproduces CPU-branch defects D1 (index shift,
+ * :213-216) and D2 (sign, :344) for forensic comparison only. */
+void orc_adjoint_advection_no_dealias(double *fx, double *fy, double *fz,
+                                      const double *vx, const double *vy, const double *vz,
+                                      const double *vxb, const double *vyb, const double *vzb,
+                                      int lx, int nelv, const double *D, const double *w,
+                                      double *const G[9], int bug_compat);
+/* adv_adjoint_no_dealias.f90:365-427 (linearised operator; used for the adjoint identity) */
+void orc_linear_advection_no_dealias(double *fx, double *fy, double *fz,
+                                     const double *vx, const double *vy, const double *vz,
+                                     const double *vxb, const double *vyb, const double *vzb,
+                                     int lx, int nelv, const double *D, const double *w,
+                                     double *const G[9], const double *jac);
+/* adv_adjoint_dealias.f90:137-161 + 235-462 (CPU branch with per-element geometry).
+ * lxd = fine GL order; GLL-space G is interpolated to GL as init_dealias does. */
+void orc_adjoint_advection_dealias(double *fx, double *fy, double *fz,
+                                   const double *vx, const double *vy, const double *vz,
+                                   const double *vxb, const double *vyb, const double *vzb,
+                                   int lx, int lxd, int nelv, double *const G[9]);
+/* adv_adjoint_dealias.f90:479-668 (linearised operator, dealiased) */
+void orc_linear_advection_dealias(double *fx, double *fy, double *fz,
+                                  const double *vx, const double *vy, const double *vz,
+                                  const double *vxb, const double *vyb, const double *vzb,
+                                  int lx, int lxd, int nelv, double *const G[9]);
+
+/* RAMP_mapping.f90:182-196 (convex down) / :227-241 (convex up) */
+void orc_ramp(double *chi, const double *rho, int64_t n, double f_min, double f_max, double q,
+              int convex_up);
+/* RAMP_mapping.f90:203-222 / :248-267 chain rule */
+void orc_ramp_backward(double *dF_drho, const double *dF_dchi, const double *rho, int64_t n,
+                       double f_min, double f_max, double q, int convex_up);
+/* simple_brinkman_source_term.f90:139-153: f_i -= chi*u_i */
+void orc_brinkman(double *fx, double *fy, double *fz, const double *u, const double *v,
+                  const double *w, const double *chi, int64_t n);
+/* adjoint_lube_source_term.f90:173-206: f_i += (K*chi [masked]) * u_i; mask = 1-based indices
+ * kept (mask_ops.f90:55-82), everything else zeroed; mask==NULL -> no mask */
+void orc_lube(double *fx, double *fy, double *fz, const double *u, const double *v,
+              const double *w, const double *chi, double K, const int *mask, int mask_size,
+              int64_t n);
+/* adjoint_pnpn.f90:671-676: f_i *= B */
+void orc_opcolv(double *fx, double *fy, double *fz, const double *B, int64_t n);
+/* minimum_dissipation_objective_function.f90:260-301 */
+void orc_sensitivity(double *S, const double *u, const double *v, const double *w,
+                     const double *ua, const double *va, const double *wa, double K_obj,
+                     int if_lube, int64_t n);
+
+/* The whole explicit-RHS slice adjoint_pnpn.f90:661-682:
+ *   f = 0; brinkman(u_adj, chi); [lube(u_b, chi)]; [f += f_static]; f *= B; adv%compute_adjoint.
+ * chi = RAMP(rho) if chi_in == NULL.  sens may be NULL.  lxd == 0 -> no dealias. */
+typedef struct {
+  double f_min, f_max, q;
+  int convex_up;
+  int if_lube;
+  double K_lube;  /* K*obj_scale handed to the lube term (min_diss_objective :158-166) */
+  double K_sens;  /* K*obj_scale in the sensitivity (:295-296) */
+  int lxd;
+} orc_params;
+void orc_adjoint_rhs(double *fx, double *fy, double *fz, double *sens, double *chi_out,
+                     const double *vx, const double *vy, const double *vz,
+                     const double *vxb, const double *vyb, const double *vzb,
+                     const double *rho, const double *chi_in,
+                     const double *fsx, const double *fsy, const double *fsz,
+                     const int *mask, int mask_size,
+                     int lx, int nelv, const double *D, const double *w,
+                     double *const G[9], const double *B, const orc_params *p);
+
+/* ---- gather-scatter (Neko gs_t%op(., GS_OP_ADD); adjoint_pnpn.f90:725,755-757) -------------- */
+/* class_id[n]: canonical relabelling -- classes numbered by first appearance (ascending dof).
+ * returns number of classes. */
+int64_t orc_gs_classes(int64_t *class_id, const int64_t *key, int64_t n);
+/* in-place direct-stiffness sum; members summed in ascending dof order */
+void orc_gs_add(double *f, const int64_t *class_id, int64_t nclass, int64_t n);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- adjoint-RHS throughput (GDOF/s, fp64, lx=8) of the B200 path, one process per GPU.
+
+A "step" is one fused evaluation of the hot path over one rank's brick of synthetic input:
+source terms (RAMP + Brinkman + lube) -> mass matrix -> adjoint advection -> sensitivity, then
+gs_op(f_i, GS_OP_ADD) on the three components incl. the NCCL shared-node exchange
+(/root/reference/sources/adjoint/adjoint_pnpn.f90:669-682 + :755-757).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--ne 64] [--lx 8] [--impl reference]
+
+Workload (BASELINE.json configs[3], the configuration the metric "GDOF/s at 1/2/4/8 B200" is quoted
+on; it fits one GPU): 64^3 hexahedra per GPU, lx=8, global box (64 px) x (64 py) x (64 pz), fields keyed
+on the global node lattice.  `--ne 32` gives configs[1].  All 21 fields (2.8 GB at 32^3, 22.5 GB at
+64^3) are far larger than the 126 MB L2, so no L2 flush is needed between timed iterations.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the reference itself -- Fortran
+on top of un-vendored Neko -- cannot be built here) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "adjoint-RHS GDOF/s (fp64, lx=8)"
+UNIT = "GDOF/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ne", type=int, default=64, help="elements per direction per GPU")
+    ap.add_argument("--lx", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample-ne", type=int, default=16)
+    return ap.parse_args()
+
+
+def workload_name(ne, lx, n):
+    tag = "configs[3]" if ne == 64 and lx == 8 else ("configs[1]" if ne == 32 and lx == 8 and n == 1 else "custom")
+    return f"{tag}: synthetic box {ne}^3 hex elements per GPU, lx={lx}, random design field rho"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sampled with NVML from a thread DURING the timed region
+# ------------------------------------------------------------------------------------------------
+_REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+            0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:     # pragma: no cover
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in _REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.ok:
+            self._stop.set()
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: oracle on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_problem(ne_gpu, lx, sample_ne, px=1, py=1, pz=1):
+    """sample_ne^3 elements cut from the corner of rank 0's brick of the same global mesh, same field
+    generators (keyed on the global node lattice)."""
+    import torch
+    import neko_top_b200  # noqa: F401
+    from neko_top_b200 import sem, workloads
+    s = min(sample_ne, ne_gpu)
+    brick = workloads.BoxBrick(lx=lx, ne=(s, s, s), ne_global=(ne_gpu * px, ne_gpu * py, ne_gpu * pz),
+                               length=(float(px), float(py), float(pz)), name="cpu sample")
+    sp = sem.Space(lx)
+    x, y, z = workloads.coords(brick)
+    keys = workloads.node_keys(brick)
+    G, _, B = sem.geometric_factors(x, y, z, sp)
+    fl = workloads.make_fields(brick, x, y, z, keys)
+    f = lambda a: a.reshape(-1).numpy()
+    return dict(brick=brick, sp=sp, G=[f(g) for g in G], B=f(B), v=[f(a) for a in fl.v], ub=[f(a) for a in fl.ub],
+                rho=f(fl.rho), key=f(keys), desc=f"{s}^3-element corner brick of the same mesh and fields "
+                                                f"({brick.n} DOF per step)")
+
+
+def time_oracle(prob, steps, warmup, budget_s=None):
+    from oracle import pyoracle as orc
+    orc.build()
+    b = prob["brick"]
+    st = orc.RhsStep(prob["v"], prob["ub"], prob["rho"], b.lx, b.nelv, prob["sp"].dx, prob["sp"].wx, prob["G"],
+                     prob["B"], prob["key"])
+    for _ in range(warmup):
+        st.step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        st.step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return b.n * done / dt / 1e9, dt / done * 1e3, done, orc.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from neko_top_b200 import workloads
+    px, py, pz = workloads.rank_grid(args.gpus)
+    prob = cpu_sample_problem(args.ne, args.lx, args.cpu_sample_ne, px, py, pz)
+    val, ms, done, threads = time_oracle(prob, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.ne, args.lx, args.gpus), "lx": args.lx,
+                   "elements_per_gpu": args.ne ** 3},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": prob["desc"] + "; oracle/oracle.c (OpenMP over elements); the Fortran/Neko "
+                                                  "reference cannot be built in this image"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 side
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import neko_top_b200  # noqa: F401
+    from neko_top_b200 import operators as ops, partition, sem, workloads
+
+    N = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != N:
+        raise SystemExit(f"--gpus {N} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {N}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: neko_top_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if N > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lx, ne = args.lx, args.ne
+    brick = workloads.config_weak(rank, N, ne, lx)
+    sp = sem.Space(lx)
+    x, y, z = workloads.coords(brick, dev)
+    keys = workloads.node_keys(brick, dev).reshape(-1)
+    G, jac, B = sem.geometric_factors(x, y, z, sp, chunk=8192)
+    fl = workloads.make_fields(brick, x, y, z, keys.view(brick.nelv, lx, lx, lx))
+    del x, y, z, jac
+    flat = lambda a: a.reshape(-1).contiguous()
+    G, B = [flat(g) for g in G], flat(B)
+    v, ub, rho = [flat(a) for a in fl.v], [flat(a) for a in fl.ub], flat(fl.rho)
+    del fl
+    n = brick.n
+    f = [torch.empty(n, device=dev, dtype=torch.float64) for _ in range(3)]
+    sens = torch.empty(n, device=dev, dtype=torch.float64)
+
+    coef = ops.coef_t(ops.space_t(lx, sp.dx, sp.wx), brick.nelv, G, B)
+    op = ops.fused_adjoint_rhs_t(coef, device=local)
+    op.set_params()                         # RAMP 0/1000/1 convex-up, K = 1, obj_scale = 1
+    op.gs.init(keys)
+    if N > 1:
+        idb = [ops.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(idb, src=0)
+        op.comm_init(idb[0], rank, N)
+        cand = workloads.interface_candidates(brick, dev)
+        sh = partition.find_shared_nodes(keys, cand, lx ** 3, rank, N)
+        del cand
+        op.gs.init_shared(sh.shared_dof, sh.neigh_rank, sh.neigh_off, sh.neigh_idx)
+        op.set_boundary_elements(sh.bnd_elem)
+    del keys
+    torch.cuda.empty_cache()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(val):
+        if N == 1:
+            return val
+        t = torch.tensor([val], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumr(val):
+        if N == 1:
+            return val
+        t = torch.tensor([val], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing: `value` ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        op.step(v, ub, f, rho=rho, sens=sens)
+    barrier()
+    clk = ClockSampler(local)
+    op.enable_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ops.launch_count()
+    clk.start()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        op.step(v, ub, f, rho=rho, sens=sens)
+    e1.record()
+    barrier()
+    clk.stop()
+    launches = ops.launch_count() - l0
+    ms_total = maxr(e0.elapsed_time(e1))
+    elem_ms, gs_ms, nmarks = op.get_timing()
+    op.enable_timing(False)
+    ms_step = ms_total / args.steps
+    n_global = sumr(float(n))
+    value = n_global / (ms_step * 1e-3) / 1e9
+    launches_all = int(sumr(float(launches)))
+    checksum = float(sum(float(t.double().abs().sum().item()) for t in f))
+
+    # ---- e2e: host buffers through the C ABI ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hv = [t.cpu().pin_memory() for t in v]
+        hub = [t.cpu().pin_memory() for t in ub]
+        hrho = rho.cpu().pin_memory()
+        hf = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+        hs = torch.empty(n, dtype=torch.float64).pin_memory()
+        op.step_host(hv, hub, hrho, hf, hs)           # warm-up (allocates the staging buffers)
+        op.step_host(hv, hub, hrho, hf, hs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            op.step_host(hv, hub, hrho, hf, hs)
+        torch.cuda.synchronize()
+        dt = maxr(time.perf_counter() - t0)
+        barrier()
+        e2e_ok = all(bool(torch.equal(hf[c], f[c].cpu())) for c in range(3)) and bool(torch.equal(hs, sens.cpu()))
+        e2e = {"value": n_global / (dt / args.e2e_steps) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(7 * n * 8), "d2h_bytes_per_step": int(4 * n * 8),
+               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "matches_device_path": bool(e2e_ok),
+               "note": "b200_adjrhs_step_host: 7 input fields H2D from pinned memory, f(3)+sens D2H, "
+                       "geometry resident (set once like coef_t); bytes are per rank"}
+        del hv, hub, hrho, hf, hs
+
+    # ---- roofline of the dominant kernel (rank 0) ------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bpd = sem.algorithmic_bytes_per_dof(lx, with_gs=False)
+    achieved = n * bpd / (elem_ms * 1e-3) / 1e9 if elem_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"ne{ne}_lx{lx}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "kernel": "adjrhs_fused_kernel (element kernel; 168 B/DOF algorithmic)",
+                "kernel_ms": elem_ms, "gs_ms": gs_ms, "algorithmic_bytes_per_launch": n * bpd,
+                "peak_source": peak_src,
+                "step_GBps": n * sem.algorithmic_bytes_per_dof(lx, True) / (ms_step * 1e-3) / 1e9}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu:
+        prob = cpu_sample_problem(ne, lx, args.cpu_sample_ne)
+        cval, cms, cdone, threads = time_oracle(prob, 40, 2, budget_s=12.0)
+        cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": prob["desc"] + f"; {cdone} steps of oracle/oracle.c, {cms:.1f} ms each"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(ne, lx, N), "lx": lx, "elements_per_gpu": ne ** 3,
+                       "dof_per_gpu": n, "rank_grid": list(workloads.rank_grid(N)),
+                       "l2": "inputs (21 fields, %.1f GB per GPU) exceed the 126 MB L2; no flush needed"
+                             % (21 * n * 8 / 1e9)},
+            "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk.summary(), "checksum_abs_f": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    op.free()
+    if N > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -107,7 +107,8 @@ struct Handle {
 
   // timing
   bool timing = false;
-  std::vector<cudaEvent_t> tev;   // (start, mid, end) triples: elem kernel = mid-start, gs = end-mid
+  std::vector<cudaEvent_t> tev;   // pool of (start, mid, end) triples: elem kernel = mid-start, gs = end-mid
+  size_t tev_n = 0;               // events of the pool recorded since timing was enabled
 };
 
 Handle* H(void* h) { return reinterpret_cast<Handle*>(h); }
@@ -229,11 +230,13 @@ int check_fields(std::initializer_list<const void*> ps) {
 
 int time_mark(Handle* h) {
   if (!h->timing) return B200_OK;
-  if (h->tev.size() >= 3 * 4096) return B200_OK;
-  cudaEvent_t e;
-  CK(cudaEventCreate(&e));
-  CK(cudaEventRecord(e, h->stream));
-  h->tev.push_back(e);
+  if (h->tev_n >= 3 * 4096) return B200_OK;
+  if (h->tev_n == h->tev.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->tev.push_back(e);
+  }
+  CK(cudaEventRecord(h->tev[h->tev_n++], h->stream));
   return B200_OK;
 }
 
@@ -1012,8 +1015,15 @@ int b200_adjrhs_enable_timing(void* handle, const int* flag) {
   if (!handle) return fail(B200_ERR_ARG, "null handle");
   Handle* h = H(handle);
   h->timing = flag && *flag;
-  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
-  h->tev.clear();
+  h->tev_n = 0;
+  if (h->timing) {   // pre-create the pool so no event is created inside a timed region
+    CK(cudaSetDevice(h->device));
+    while (h->tev.size() < 3 * 256) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->tev.push_back(e);
+    }
+  }
   return B200_OK;
 }
 
@@ -1023,7 +1033,7 @@ int b200_adjrhs_get_timing(void* handle, double* elem_kernel_ms, double* gs_ms, 
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   double a = 0.0, b = 0.0;
-  const size_t nt = h->tev.size() / 3;
+  const size_t nt = h->tev_n / 3;
   for (size_t i = 0; i < nt; i++) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->tev[3 * i], h->tev[3 * i + 1])); a += ms;

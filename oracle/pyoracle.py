@@ -258,3 +258,32 @@ def gs_add(f, cid, nclass):
     f = f64(f).copy()
     lib().orc_gs_add(_p(f), cid.ctypes.data_as(_lp), C.c_int64(nclass), C.c_int64(f.size))
     return f
+
+
+class RhsStep:
+    """Pre-bound arguments for repeated timing of one oracle "step" = orc_adjoint_rhs (source terms,
+    mass matrix, adjoint advection, sensitivity) + orc_gs_add on the three components, i.e. the CPU
+    restatement of adjoint_pnpn.f90:669-682 + :755-757.  Used by bench.py's cpu_baseline and
+    --impl reference legs only (the one place outside tests/ that may execute oracle/)."""
+
+    def __init__(self, v, vb, rho, lx, nelv, D, w, G, B, key, **kw):
+        self.lx, self.nelv, self.n = lx, nelv, lx ** 3 * nelv
+        self.a = dict(v=[f64(x) for x in v], vb=[f64(x) for x in vb], rho=f64(rho), D=_colmajor(D), w=f64(w),
+                      G=[f64(g) for g in G], B=f64(B))
+        self.f = [np.zeros(self.n) for _ in range(3)]
+        self.sens = np.zeros(self.n)
+        self.chi = np.zeros(self.n)
+        self.p = params(kw.get("f_min", 0.0), kw.get("f_max", 1000.0), kw.get("q", 1.0), kw.get("convex_up", 1),
+                        kw.get("if_lube", 1), kw.get("K_lube", 1.0), kw.get("K_sens", 1.0), kw.get("lxd", 0))
+        self.cid, self.nc = gs_classes(key)
+        self.Gp = _G(self.a["G"])
+
+    def step(self):
+        a, L = self.a, lib()
+        L.orc_adjoint_rhs(_p(self.f[0]), _p(self.f[1]), _p(self.f[2]), _p(self.sens), _p(self.chi),
+                          _p(a["v"][0]), _p(a["v"][1]), _p(a["v"][2]), _p(a["vb"][0]), _p(a["vb"][1]),
+                          _p(a["vb"][2]), _p(a["rho"]), None, None, None, None, None, C.c_int(0),
+                          C.c_int(self.lx), C.c_int(self.nelv), _p(a["D"]), _p(a["w"]), self.Gp, _p(a["B"]),
+                          C.byref(self.p))
+        for c in range(3):
+            L.orc_gs_add(_p(self.f[c]), self.cid.ctypes.data_as(_lp), C.c_int64(self.nc), C.c_int64(self.n))

@@ -1,0 +1,78 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads here (no GPU needed) and exports every
+symbol include/neko_top_b200.h declares; argument errors come back as status codes with a message;
+with no CUDA device the library refuses to create a handle (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import neko_top_b200  # noqa: F401
+from neko_top_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "neko_top_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    _lib.build()
+    return _lib.lib()
+
+
+def test_exports_match_header(L):
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "loader table and header disagree"
+
+
+def test_version_and_error_reporting(L):
+    assert L.b200_version() >= 100
+    _lib.set_abort_on_error(0)
+    try:
+        h = C.c_void_p()
+        rc = L.b200_adjrhs_create(C.byref(h), C.byref(C.c_int(3)), C.byref(C.c_int(8)), C.byref(C.c_int(0)))
+        assert rc == 1 and b"lx=3" in L.b200_last_error()
+        rc = L.b200_adjrhs_compute(None, *([None] * 16))
+        assert rc == 1
+    finally:
+        _lib.set_abort_on_error(1)
+
+
+def test_no_cpu_fallback(L):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    _lib.set_abort_on_error(0)
+    try:
+        h = C.c_void_p()
+        rc = L.b200_adjrhs_create(C.byref(h), C.byref(C.c_int(8)), C.byref(C.c_int(8)), C.byref(C.c_int(0)))
+        assert rc == 2 and not h.value
+        assert b"no CPU fallback" in L.b200_last_error()
+    finally:
+        _lib.set_abort_on_error(1)
+
+
+def test_product_never_imports_oracle():
+    """The package and bench's product arm must not reach into oracle/."""
+    pkg = os.path.join(ROOT, "neko-top_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".f90")):
+                src = open(os.path.join(dp, f)).read()
+                assert "pyoracle" not in src and "np_oracle" not in src and "liboracle" not in src, f
+
+
+def test_fortran_shim_binds_every_symbol():
+    """fortran/neko_top_b200.f90 declares a bind(c) interface for each exported entry point."""
+    path = os.path.join(ROOT, "neko-top_b200", "fortran", "neko_top_b200.f90")
+    src = open(path).read().lower()
+    for n in _declared():
+        assert f"name='{n}'" in src or f'name="{n}"' in src, f"{n} missing from the Fortran interface block"

@@ -38,3 +38,259 @@ def test_fused_rhs_matches_oracle(oracle, lx):
     assert rel_l2(sens.cpu().numpy(), so) <= TOL
     assert np.array_equal(chi.cpu().numpy(), co), "RAMP map must be bit-exact"
     op.free()
+
+
+def _nan(n):
+    return torch.full((n,), float("nan"), device="cuda", dtype=torch.float64)
+
+
+@pytest.mark.parametrize("lx", [6, 8])
+def test_fused_variants(oracle, lx):
+    """chi given instead of rho; static forcing; lube off; convex-down RAMP; masked lube."""
+    P = Problem(lx, ne=(2, 3, 2), deform=0.03)
+    rng = np.random.default_rng(5)
+    op, _ = _fused(P)
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    # (a) chi_in + f_static
+    chi = rng.random(P.n) * 1000.0
+    fs = [rng.standard_normal(P.n) for _ in range(3)]
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, chi=chi, fstatic=fs)
+    f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+    op.compute(v, ub, f, chi=torch.as_tensor(chi).cuda(), fstatic=[torch.as_tensor(a).cuda() for a in fs], sens=sens)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    # (b) lube off, convex-down RAMP, other constants
+    op.set_params(f_min=2.0, f_max=500.0, q=0.5, convex_up=False, if_lube=False)
+    fo, so, co = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho, f_min=2.0,
+                                    f_max=500.0, q=0.5, convex_up=0, if_lube=0)
+    f, sens, chio = [_nan(P.n) for _ in range(3)], _nan(P.n), _nan(P.n)
+    op.compute(v, ub, f, rho=rho, sens=sens, chi_out=chio)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    assert np.array_equal(chio.cpu().numpy(), co)
+    # (c) masked lube (1-based point-zone indices), K = 2.5
+    op.set_params(if_lube=True, K_lube=2.5, K_sens=2.5)
+    mask = (np.sort(rng.choice(P.n, P.n // 7, replace=False)) + 1).astype(np.int32)
+    op.set_lube_mask(torch.as_tensor(mask).cuda())
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho, mask=mask,
+                                   K_lube=2.5, K_sens=2.5)
+    f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+    op.compute(v, ub, f, rho=rho, sens=sens)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    op.free()
+
+
+@pytest.mark.parametrize("lx", [5, 8])
+def test_advection_adjoint_plugin(oracle, lx):
+    """advection_adjoint_t%compute_adjoint drop-in: f is in/out (accumulated)."""
+    ops = _ops()
+    P = Problem(lx, ne=(2, 2, 2), deform=0.03)
+    rng = np.random.default_rng(8)
+    f0 = [rng.standard_normal(P.n) for _ in range(3)]
+    fo = oracle.adjoint_advection_no_dealias(f0, P.v, P.ub, lx, P.nelv, P.D, P.w, P.G)
+    coef = ops.coef_t(ops.space_t(P.lx, P.D, P.w), P.nelv, P.cuda("G"), P.cuda("B"))
+    adv = ops.advection_adjoint_factory({"case": {"numerics": {"dealias": False, "polynomial_order": lx - 1}}}, coef)
+    f = [torch.as_tensor(a).cuda() for a in f0]
+    v, ub = P.cuda("v"), P.cuda("ub")
+    adv.compute_adjoint(*v, *ub, *f, n=P.n)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    adv.free()
+
+
+def test_unfused_pointwise_plugins(oracle):
+    """The reference's call order with the un-fused drop-ins: source_term%compute (Brinkman, lube),
+    opcolv, compute_adjoint, compute_sensitivity == the fused kernel == the oracle."""
+    ops = _ops()
+    lx = 7
+    P = Problem(lx, ne=(2, 2, 3), deform=0.03)
+    fo, so, co = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    v, ub, rho, B = P.cuda("v"), P.cuda("ub"), P.cuda("rho"), P.cuda("B")
+    chi = _nan(P.n)
+    ops.RAMP_mapping_t().apply_forward(chi, rho)
+    assert np.array_equal(chi.cpu().numpy(), co)
+    f = [torch.zeros(P.n, device="cuda", dtype=torch.float64) for _ in range(3)]
+    br = ops.simple_brinkman_source_term_t()
+    br.init_from_components(*f, chi, *v, None)
+    br.compute_()
+    lu = ops.adjoint_lube_source_term_t()
+    lu.init_from_components(*f, chi, 1.0, *ub)
+    lu.compute_()
+    ops.opcolv(*f, B)
+    coef = ops.coef_t(ops.space_t(P.lx, P.D, P.w), P.nelv, P.cuda("G"), B)
+    adv = ops.advection_adjoint_factory({"case": {"numerics": {"dealias": False}}}, coef)
+    adv.compute_adjoint(*v, *ub, *f)
+    sens = _nan(P.n)
+    ops.compute_sensitivity(sens, *ub, *v)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    # RAMP backward
+    dF = torch.as_tensor(np.linspace(-1, 1, P.n)).cuda()
+    out = _nan(P.n)
+    ops.RAMP_mapping_t().apply_backward(out, dF, rho)
+    assert rel_l2(out.cpu().numpy(), oracle.ramp_backward(dF.cpu().numpy(), P.rho)) <= 1e-15
+    adv.free()
+
+
+@pytest.mark.parametrize("lx,ne", [(4, (3, 2, 2)), (8, (3, 3, 2)), (5, (1, 1, 1))])
+def test_gs_index_maps_bit_exact(oracle, lx, ne):
+    """Node classes of the GPU gather-scatter == the oracle's, after the canonical relabelling
+    (exact integer comparison)."""
+    P = Problem(lx, ne=ne, deform=0.0)
+    op, _ = _fused(P)
+    key = P.keys.reshape(-1)
+    op.gs.init(key.cuda())
+    cid, nc = op.gs.classes()
+    cido, nco = oracle.gs_classes(key.numpy())
+    assert nc == nco and np.array_equal(cid, cido)
+    # host-key path gives the same map
+    op.gs.init(key.numpy())
+    cid2, nc2 = op.gs.classes()
+    assert nc2 == nco and np.array_equal(cid2, cido)
+    op.free()
+
+
+def test_gs_op_parity_and_properties(oracle):
+    lx = 6
+    P = Problem(lx, ne=(3, 2, 2), deform=0.0)
+    op, _ = _fused(P)
+    key = P.keys.reshape(-1)
+    op.gs.init(key.cuda())
+    cido, nco = oracle.gs_classes(key.numpy())
+    rng = np.random.default_rng(1)
+    f = [rng.standard_normal(P.n) for _ in range(3)]
+    g = [torch.as_tensor(a).cuda() for a in f]
+    op.gs.op3(*g)
+    for c in range(3):
+        assert np.array_equal(g[c].cpu().numpy(), oracle.gs_add(f[c], cido, nco)), "same summation order => bit-exact"
+    one = torch.as_tensor(f[0]).cuda()
+    op.gs.op(one)
+    assert np.array_equal(one.cpu().numpy(), g[0].cpu().numpy())
+    mult = torch.ones(P.n, device="cuda", dtype=torch.float64)
+    op.gs.op(mult)
+    assert mult.min().item() == 1 and mult.max().item() == 8
+    again = (g[1] / mult).clone()
+    op.gs.op(again)
+    assert rel_l2(again.cpu().numpy(), g[1].cpu().numpy()) <= 1e-14
+    op.free()
+
+
+@pytest.mark.parametrize("lx", [6, 8])
+def test_step_matches_oracle(oracle, lx):
+    """One bench "step": fused kernel + gs_op on f."""
+    P = Problem(lx, ne=(3, 3, 2), deform=0.03)
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
+    op, _ = _fused(P)
+    op.gs.init(P.keys.reshape(-1).cuda())
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+    op.step(v, ub, f, rho=rho, sens=sens)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), oracle.gs_add(fo[c], cid, nc)) <= TOL
+    # host-buffer entry point (bench e2e) gives the identical result
+    hv = [a.cpu().pin_memory() for a in v]
+    hub = [a.cpu().pin_memory() for a in ub]
+    hf = [torch.empty(P.n, dtype=torch.float64).pin_memory() for _ in range(3)]
+    hs = torch.empty(P.n, dtype=torch.float64).pin_memory()
+    op.step_host(hv, hub, rho.cpu().pin_memory(), hf, hs)
+    for c in range(3):
+        assert torch.equal(hf[c], f[c].cpu())
+    assert torch.equal(hs, sens.cpu())
+    op.free()
+
+
+def test_golden_fixture_gpu():
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adjrhs_lx4.json")))
+    P = Problem(g["lx"], ne=tuple(g["ne"]), deform=g["deform"])
+    op, _ = _fused(P)
+    f, sens, chi = [_nan(P.n) for _ in range(3)], _nan(P.n), _nan(P.n)
+    op.compute(P.cuda("v"), P.cuda("ub"), f, rho=P.cuda("rho"), sens=sens, chi_out=chi)
+    idx = np.asarray(g["idx"])
+    for c in range(3):
+        assert np.allclose(f[c].cpu().numpy()[idx], g["f"][c], rtol=1e-12, atol=1e-13)
+    assert np.allclose(sens.cpu().numpy()[idx], g["sens"], rtol=1e-13, atol=1e-14)
+    assert np.allclose(chi.cpu().numpy()[idx], g["chi"], rtol=1e-14)
+    op.free()
+
+
+def test_duct_configs(oracle):
+    """BASELINE configs[0] (lx=6) and configs[2] (lx=8): duct 24x8x8, chi = 1000 in the lowperm box."""
+    from neko_top_b200 import sem, workloads
+    ops = _ops()
+    for lx in (6, 8):
+        brick = workloads.config_duct(lx)
+        sp = sem.Space(lx)
+        x, y, z = workloads.coords(brick, "cuda")
+        keys = workloads.node_keys(brick, "cuda")
+        G, _, B = sem.geometric_factors(x, y, z, sp)
+        fl = workloads.make_fields(brick, x, y, z, keys)
+        chi = workloads.brinkman_zone_chi(x, y, z)
+        flat = lambda a: a.reshape(-1).contiguous()
+        Gf, Bf, v, ub, chif = [flat(g) for g in G], flat(B), [flat(a) for a in fl.v], [flat(a) for a in fl.ub], flat(chi)
+        op = ops.fused_adjoint_rhs_t(ops.coef_t(ops.space_t(lx, sp.dx, sp.wx), brick.nelv, Gf, Bf))
+        op.gs.init(flat(keys))
+        f, sens = [_nan(brick.n) for _ in range(3)], _nan(brick.n)
+        op.step(v, ub, f, chi=chif, sens=sens)
+        c = lambda t: t.cpu().numpy()
+        fo, so, _ = oracle.adjoint_rhs([c(a) for a in v], [c(a) for a in ub], lx, brick.nelv, sp.dx, sp.wx,
+                                       [c(g) for g in Gf], c(Bf), chi=c(chif))
+        cid, nc = oracle.gs_classes(c(flat(keys)))
+        for k in range(3):
+            assert rel_l2(c(f[k]), oracle.gs_add(fo[k], cid, nc)) <= TOL
+        assert rel_l2(c(sens), so) <= TOL
+        op.free()
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] (32^3, lx=8) through size-independent properties: linearity in the adjoint
+    velocity, sum conservation of the direct-stiffness sum, determinism."""
+    from neko_top_b200 import sem, workloads
+    ops = _ops()
+    lx, ne = 8, 32
+    brick = workloads.config_box(ne, lx)
+    sp = sem.Space(lx)
+    x, y, z = workloads.coords(brick, "cuda")
+    keys = workloads.node_keys(brick, "cuda")
+    G, _, B = sem.geometric_factors(x, y, z, sp)
+    fl = workloads.make_fields(brick, x, y, z, keys)
+    fl2 = workloads.make_fields(brick, x, y, z, keys + 12345)
+    del x, y, z
+    flat = lambda a: a.reshape(-1).contiguous()
+    op = ops.fused_adjoint_rhs_t(ops.coef_t(ops.space_t(lx, sp.dx, sp.wx), brick.nelv, [flat(g) for g in G], flat(B)))
+    op.gs.init(flat(keys))
+    v1, v2, ub, rho = [flat(a) for a in fl.v], [flat(a) for a in fl2.v], [flat(a) for a in fl.ub], flat(fl.rho)
+    n = brick.n
+    mk = lambda: [torch.empty(n, device="cuda", dtype=torch.float64) for _ in range(3)]
+    a, b = 0.75, -1.5
+    f1, f2, fm = mk(), mk(), mk()
+    op.compute(v1, ub, f1, rho=rho)
+    op.compute(v2, ub, f2, rho=rho)
+    op.compute([a * p + b * q for p, q in zip(v1, v2)], ub, fm, rho=rho)
+    for c in range(3):
+        ref = a * f1[c] + b * f2[c]
+        assert (torch.linalg.norm(fm[c] - ref) / torch.linalg.norm(ref)).item() <= 1e-12   # inputs a*v1+b*v2 are themselves rounded; D amplifies by ~lx^2
+    # determinism
+    f1b = mk()
+    op.compute(v1, ub, f1b, rho=rho)
+    assert all(torch.equal(p, q) for p, q in zip(f1, f1b))
+    # gs conserves the multiplicity-weighted sum and makes the field C0
+    mult = torch.ones(n, device="cuda", dtype=torch.float64)
+    op.gs.op(mult)
+    s0 = f1[0].sum().item()
+    g = f1[0].clone()
+    op.gs.op(g)
+    assert abs((g / mult).sum().item() - s0) <= 1e-9 * f1[0].abs().sum().item()
+    k = flat(keys)
+    order = torch.argsort(k)
+    ks, gsrt = k[order], g[order]
+    same = ks[1:] == ks[:-1]
+    assert torch.equal(gsrt[1:][same], gsrt[:-1][same])
+    op.free()

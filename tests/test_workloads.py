@@ -1,0 +1,65 @@
+"""CPU tests of the host-side workload generators (product-side host logic)."""
+import numpy as np
+import torch
+
+import neko_top_b200  # noqa: F401
+from neko_top_b200 import sem, workloads
+
+
+def test_hash_uniform_matches_numpy_twin():
+    k = torch.arange(0, 100000, 37, dtype=torch.int64) * 7919 + 13
+    for seed in (1234, 4321):
+        a = workloads.hash_uniform(k, seed).numpy()
+        b = workloads.hash_uniform_numpy(k.numpy(), seed)
+        assert np.array_equal(a, b)
+        assert 0.0 <= a.min() and a.max() < 1.0 and abs(a.mean() - 0.5) < 0.02
+
+
+def test_fields_are_c0_and_partition_independent():
+    """Fields are functions of the global node: a rank's brick reproduces the global values exactly."""
+    lx = 5
+    whole = workloads.BoxBrick(lx=lx, ne=(4, 2, 2), ne_global=(4, 2, 2), length=(2.0, 1.0, 1.0))
+    xw, yw, zw = workloads.coords(whole)
+    kw = workloads.node_keys(whole)
+    fw = workloads.make_fields(whole, xw, yw, zw, kw)
+    # C0: equal keys -> equal values
+    flat_k = kw.reshape(-1).numpy()
+    order = np.argsort(flat_k, kind="stable")
+    same = flat_k[order][1:] == flat_k[order][:-1]
+    for fld in [fw.rho] + fw.v + fw.ub + [xw, yw, zw]:
+        a = fld.reshape(-1).numpy()[order]
+        assert np.array_equal(a[1:][same], a[:-1][same])
+    for rank in range(2):
+        part = workloads.config_weak(rank, 2, ne_per_gpu=2, lx=lx)
+        assert part.ne_global == (4, 2, 2)
+        xp, yp, zp = workloads.coords(part)
+        kp = workloads.node_keys(part)
+        fp = workloads.make_fields(part, xp, yp, zp, kp)
+        # local element e=(ex,ey,ez) of rank r is global element (ex+2r, ey, ez)
+        e = np.arange(part.nelv)
+        ex, ey, ez = e % 2, (e // 2) % 2, e // 4
+        ge = (ex + 2 * rank) + 4 * (ey + 2 * ez)
+        assert np.array_equal(kp.numpy(), kw.numpy()[ge])
+        assert np.array_equal(fp.rho.numpy(), fw.rho.numpy()[ge])
+        assert np.array_equal(fp.v[1].numpy(), fw.v[1].numpy()[ge])
+        assert np.array_equal(xp.numpy(), xw.numpy()[ge])
+
+
+def test_configs():
+    d = workloads.config_duct(6)
+    assert d.nelv == 1536 and d.n == 331776                      # BASELINE configs[0]
+    assert workloads.config_duct(8).n == 786432                  # configs[2]
+    assert workloads.config_box(32).n == 16777216                # configs[1]
+    assert workloads.config_weak(0, 8).n == 134217728            # configs[3]
+    assert workloads.config_sweep(8).ne == (58, 58, 58)          # configs[4]
+    assert abs(sem.algorithmic_bytes_per_dof(8) - 200.4) < 0.05
+    assert sem.algorithmic_flops_per_dof(8) == 424
+
+
+def test_brinkman_zone():
+    d = workloads.config_duct(4)
+    x, y, z = workloads.coords(d)
+    chi = workloads.brinkman_zone_chi(x, y, z)
+    assert set(np.unique(chi.numpy())) == {0.0, 1000.0}
+    inside = chi > 0
+    assert float(x[inside].min()) >= 4.75 and float(x[inside].max()) <= 5.25 and float(z[inside].max()) <= 0.0

@@ -1,0 +1,106 @@
+"""Multi-GPU parity check (run under torch.distributed.run, one process per GPU):
+every rank computes the fused step on its brick with the NCCL shared-node exchange, rank-local results
+are compared with the CPU oracle evaluated on the UNDIVIDED global mesh (oracle = checker only).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29511 tools/mgpu_check.py [ne_per_gpu] [lx]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import neko_top_b200  # noqa: E402,F401
+from neko_top_b200 import operators as ops, partition, sem, workloads  # noqa: E402
+
+
+def main():
+    ne = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    lx = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    sp = sem.Space(lx)
+
+    def build(brick, device):
+        x, y, z = workloads.coords(brick, device)
+        keys = workloads.node_keys(brick, device)
+        G, _, B = sem.geometric_factors(x, y, z, sp)
+        fl = workloads.make_fields(brick, x, y, z, keys)
+        flat = lambda a: a.reshape(-1).contiguous()
+        return dict(G=[flat(g) for g in G], B=flat(B), v=[flat(a) for a in fl.v], ub=[flat(a) for a in fl.ub],
+                    rho=flat(fl.rho), keys=flat(keys))
+
+    brick = workloads.config_weak(rank, world, ne, lx)
+    brick.deform = 0.02
+    d = build(brick, dev)
+    op = ops.fused_adjoint_rhs_t(ops.coef_t(ops.space_t(lx, sp.dx, sp.wx), brick.nelv, d["G"], d["B"]), device=local)
+    op.gs.init(d["keys"])
+    idb = [ops.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(idb, src=0)
+    op.comm_init(idb[0], rank, world)
+    sh = partition.find_shared_nodes(d["keys"], workloads.interface_candidates(brick, dev), lx ** 3, rank, world)
+    op.gs.init_shared(sh.shared_dof, sh.neigh_rank, sh.neigh_off, sh.neigh_idx)
+    n = brick.n
+    mk = lambda: [torch.full((n,), float("nan"), device=dev, dtype=torch.float64) for _ in range(3)]
+    results = {}
+    for mode in ("sequential", "overlap"):
+        if mode == "overlap":
+            op.set_boundary_elements(sh.bnd_elem)
+        f, sens = mk(), torch.empty(n, device=dev, dtype=torch.float64)
+        for _ in range(2):
+            op.step(d["v"], d["ub"], f, rho=d["rho"], sens=sens)
+        torch.cuda.synchronize()
+        results[mode] = [a.cpu().numpy() for a in f] + [sens.cpu().numpy()]
+    # host-buffer path
+    hv = [a.cpu().pin_memory() for a in d["v"]]
+    hub = [a.cpu().pin_memory() for a in d["ub"]]
+    hf = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+    hs = torch.empty(n, dtype=torch.float64).pin_memory()
+    op.step_host(hv, hub, d["rho"].cpu().pin_memory(), hf, hs)
+    results["host"] = [a.numpy() for a in hf] + [hs.numpy()]
+
+    # oracle on the undivided mesh (CPU; small sizes only)
+    from oracle import pyoracle as orc
+    px, py, pz = workloads.rank_grid(world)
+    whole = workloads.BoxBrick(lx=lx, ne=(ne * px, ne * py, ne * pz), length=(float(px), float(py), float(pz)),
+                               deform=0.02)
+    w = build(whole, "cpu")
+    c = lambda t: t.numpy()
+    fo, so, _ = orc.adjoint_rhs([c(a) for a in w["v"]], [c(a) for a in w["ub"]], lx, whole.nelv, sp.dx, sp.wx,
+                                [c(g) for g in w["G"]], c(w["B"]), rho=c(w["rho"]))
+    cid, nc = orc.gs_classes(c(w["keys"]))
+    fo = [orc.gs_add(a, cid, nc) for a in fo]
+    e = np.arange(brick.nelv)
+    ex, ey, ez = e % ne + brick.offset[0], (e // ne) % ne + brick.offset[1], e // (ne * ne) + brick.offset[2]
+    ge = ex + whole.ne[0] * (ey + whole.ne[1] * ez)
+    N = lx ** 3
+    ref = [a.reshape(whole.nelv, N)[ge].reshape(-1) for a in fo] + [so.reshape(whole.nelv, N)[ge].reshape(-1)]
+    worst = 0.0
+    for mode, res in results.items():
+        for a, b in zip(res, ref):
+            err = np.linalg.norm(a - b) / np.linalg.norm(b)
+            worst = max(worst, err)
+        print(f"rank {rank} {mode}: max rel-L2 vs global oracle = {worst:.3e}", flush=True)
+    same = all(np.array_equal(a, b) for a, b in zip(results["sequential"], results["overlap"]))
+    same_h = all(np.array_equal(a, b) for a, b in zip(results["sequential"], results["host"]))
+    t = torch.tensor([worst, 0.0 if (same and same_h) else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ok = t[0].item() <= 1e-12 and t[1].item() == 0.0
+        print(f"MGPU_CHECK world={world} ne={ne} lx={lx} nshared(rank0)={sh.nshared} nbnd(rank0)={sh.bnd_elem.size} "
+              f"max_err={t[0].item():.3e} modes_bit_identical={t[1].item() == 0.0} -> {'PASS' if ok else 'FAIL'}",
+              flush=True)
+    op.free()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,7 +49,11 @@ int b200_adjrhs_set_stream(void* handle, void* stream);
 /* space_t: dx = Xh%dx (lx*lx, column-major D(i,j)), wx = Xh%wx (lx); HOST pointers. */
 int b200_adjrhs_set_space(void* handle, const double* dx, const double* wx);
 /* coef_t device mirrors: coef%drdx_d ... coef%dtdz_d (cofactors, J-scaled) and coef%B_d.
- * Borrowed; must stay valid while the handle is used. */
+ * Borrowed; must stay valid while the handle is used.  The call also builds (on the handle's stream,
+ * synchronously) a private per-plane interleaved image of the ten arrays for the fused kernel -- one
+ * TMA bulk copy per k-plane instead of ten -- which costs 10*n*8 bytes of device memory; geometry is
+ * constant during a Neko-TOP run (coef_t is built once, adjoint_scheme.f90:341-343), call it again if
+ * the arrays ever change.  Call b200_adjrhs_set_stream first. */
 int b200_adjrhs_set_geometry(void* handle,
                              const void* drdx, const void* dsdx, const void* dtdx,
                              const void* drdy, const void* dsdy, const void* dtdy,

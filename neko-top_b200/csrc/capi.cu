@@ -19,6 +19,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include "adjrhs_kernel.cuh"
+#include "adjrhs_kernel_v2.cuh"
 #include "gs_kernels.cuh"
 #include "pointwise_kernels.cuh"
 
@@ -70,6 +71,7 @@ struct Handle {
   double w[LX_MAX];
   const double* G[9] = {};
   const double* B = nullptr;
+  double* geom_pack = nullptr;    // private image [e][k][10][lx*lx] of G[0..8], B (adjrhs_kernel_v2.cuh)
   double f_min = 0.0, f_max = 1000.0, q = 1.0, K_lube = 1.0, K_sens = 1.0;
   int convex_up = 1, if_lube = 1;
   const int* lube_mask = nullptr;
@@ -195,9 +197,107 @@ int launch_cfg(Handle* h, const LaunchArgs& a) {
   return B200_OK;
 }
 
+
+// ---- second-generation kernel (adjrhs_kernel_v2.cuh): NE element slots + one TMA warp per SM ----------
+template <int LX, int NE, int NS, int NF, int MAXREG>
+int launch_v2_cfg(Handle* h, const LaunchArgs& a) {
+  using C = V2Cfg<LX, NE, NS, NF>;
+  static_assert(C::SMEM <= 227 * 1024, "v2 configuration exceeds the shared memory of an SM");
+  static_assert(C::NTHREADS <= 1024, "v2 configuration exceeds 1024 threads");
+  KParams2<LX> p;
+  memset(&p, 0, sizeof p);
+  for (int i = 0; i < LX * LX; i++) p.D[i] = h->D[i];
+  for (int i = 0; i < LX; i++) p.w[i] = h->w[i];
+  const size_t eoff = (size_t)a.elem_begin * C::N;
+  for (int c = 0; c < 3; c++) p.ub[c] = a.vb[c] + eoff;
+  unsigned flags = 0;
+  if (!h->geom_pack) return fail(B200_ERR_STATE, "packed geometry image missing (set_geometry)");
+  p.geom = h->geom_pack + eoff * NGEO;
+  for (int c = 0; c < 3; c++) p.pf[R_V - NGEO + c] = a.v[c] + eoff;
+  if (a.sources) {
+    p.pf[R_RHO - NGEO] = a.rho + eoff;
+    flags |= FLAG_SOURCES;
+    if (!a.rho_is_chi) flags |= FLAG_RAMP;
+    if (h->convex_up) flags |= FLAG_CONVEX_UP;
+    if (h->if_lube && h->lube_mask_size == 0) flags |= FLAG_LUBE;
+    if (a.chi_out) flags |= FLAG_CHI_OUT;
+  }
+  if constexpr (NF >= NF_FULL) {
+    if (a.fs[0]) {
+      for (int c = 0; c < 3; c++) p.pf[R_FS - NGEO + c] = a.fs[c] + eoff;
+      flags |= FLAG_FSTATIC;
+    }
+    if (a.fin[0]) {
+      for (int c = 0; c < 3; c++) p.pf[R_FIN - NGEO + c] = a.fin[c] + eoff;
+      flags |= FLAG_ACCUM;
+    }
+  } else if (a.fs[0] || a.fin[0]) {
+    return fail(B200_ERR_STATE, "internal: static forcing / accumulate mode need the NF_FULL kernel");
+  }
+  if (a.sens) flags |= FLAG_SENS;
+  int na = NGEO;
+  for (int i = 0; i < NF_FULL - NGEO; i++) na += (p.pf[i] != nullptr);
+  p.n_active = na;
+  for (int c = 0; c < 3; c++) p.f[c] = a.f[c] + eoff;
+  p.sens = a.sens ? a.sens + eoff : nullptr;
+  p.chi_out = a.chi_out ? a.chi_out + eoff : nullptr;
+  p.elem_list = a.elem_list;
+  p.nelem = a.nelem;
+  p.flags = flags;
+  p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
+  p.K_sens = h->if_lube ? h->K_sens : 0.0;
+
+  auto kern = adjrhs_v2_kernel<LX, NE, NS, NF, MAXREG>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  const int grid = std::min((a.nelem + NE - 1) / NE, h->num_sm);
+  if (grid < 1) return B200_OK;
+  kern<<<grid, C::NTHREADS, C::SMEM, h->stream>>>(p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+template <int LX, int NE, int NS, int MAXREG, int NE_FULL = NE, int NS_FULL = NS>
+int launch_v2(Handle* h, const LaunchArgs& a) {
+  if (a.fs[0] || a.fin[0]) return launch_v2_cfg<LX, NE_FULL, NS_FULL, NF_FULL, MAXREG>(h, a);
+  return launch_v2_cfg<LX, NE, NS, NF_FUSED, MAXREG>(h, a);
+}
+
+int launch_fused_v1(Handle* h, const LaunchArgs& a);
+
 int launch_fused(Handle* h, const LaunchArgs& a) {
   if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
   const int cfg = h->cfg;
+  if (cfg >= 100) return launch_fused_v1(h, a);
+  switch (h->lx) {
+    case 4: return launch_v2<4, 8, 4, 224>(h, a);
+    case 5: return launch_v2<5, 8, 2, 224>(h, a);
+    case 6: return launch_v2<6, 4, 2, 224>(h, a);
+    case 7: return launch_v2<7, 4, 2, 224>(h, a);
+    case 8:
+      switch (cfg) {
+        case 1: return launch_v2<8, 4, 2, 224>(h, a);
+        case 2: return launch_v2<8, 5, 2, 184, 4, 2>(h, a);
+        case 3: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);
+        case 4: return launch_v2<8, 4, 4, 224, 4, 2>(h, a);
+        case 5: return launch_v2<8, 3, 2, 255, 3, 2>(h, a);
+        case 6: return launch_v2<8, 3, 4, 224, 3, 4>(h, a);
+        case 7: return launch_v2<8, 2, 4, 255, 2, 4>(h, a);
+        case 8: return launch_v2<8, 2, 8, 255, 2, 4>(h, a);
+        default: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);
+      }
+    case 9: return launch_v2<9, 3, 2, 200>(h, a);
+    case 10: return launch_v2<10, 2, 2, 224>(h, a);
+    default: return fail(B200_ERR_ARG, "lx=%d not instantiated (4..10)", h->lx);
+  }
+}
+
+int launch_fused_v1(Handle* h, const LaunchArgs& a) {
+  const int cfg = h->cfg - 100;
   switch (h->lx) {
     case 4: return launch_cfg<4, 2, 2, 2, 224>(h, a);
     case 5: return launch_cfg<5, 1, 3, 2, 224>(h, a);
@@ -377,7 +477,7 @@ int b200_adjrhs_free(void** handle) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep); cudaFree(h->gs_skip);
-  cudaFree(h->gs_shared_cls);
+  cudaFree(h->gs_shared_cls); cudaFree(h->geom_pack);
   cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
   cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_bnd_elem);
   cudaFree(h->d_int_elem);
@@ -425,6 +525,20 @@ int b200_adjrhs_set_geometry(void* handle, const void* drdx, const void* dsdx, c
   if (!B) return fail(B200_ERR_ARG, "set_geometry: null B");
   h->B = (const double*)B;
   if (int r = check_fields({drdx, dsdx, dtdx, drdy, dsdy, dtdy, drdz, dsdz, dtdz, B})) return r;
+  // private per-plane interleaved image for the fused kernel (one bulk copy per plane)
+  CK(cudaSetDevice(h->device));
+  if (!h->geom_pack && h->n > 0) CK(cudaMalloc(&h->geom_pack, sizeof(double) * NGEO * (size_t)h->n));
+  if (h->n > 0) {
+    GeomPtrs gp;
+    for (int i = 0; i < 9; i++) gp.p[i] = h->G[i];
+    gp.p[9] = h->B;
+    const int threads = 256;
+    geom_pack_kernel<<<grid_for(h->n, threads, h->num_sm, 16), threads, 0, h->stream>>>(
+        gp, h->geom_pack, h->lx * h->lx, h->n);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
   h->have_geom = true;
   return B200_OK;
 }

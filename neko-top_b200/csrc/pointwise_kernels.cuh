@@ -134,6 +134,19 @@ __global__ void sensitivity_kernel(double* __restrict__ S, const double* __restr
   }
 }
 
+// one-time repack of coef_t's geometry (9 cofactors + B, separate arrays x(lx,lx,lx,nelv)) into the fused
+// kernel's per-plane interleaved image out[((e*lx + k)*10 + a)*lx*lx + p]  (p = i + lx*j)
+struct GeomPtrs { const double* p[10]; };
+__global__ void geom_pack_kernel(GeomPtrs g, double* __restrict__ out, int plane, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t pl = i / plane;            // global plane index e*lx + k
+    const int64_t pt = i - pl * plane;
+#pragma unroll
+    for (int a = 0; a < 10; a++) out[(pl * 10 + a) * plane + pt] = g.p[a][i];
+  }
+}
+
 // steady_simcomp.f90:158-176: d = old - new; acc += d*d; old = new.  One double atomic per CTA.
 __global__ void steady_update_kernel(double* __restrict__ result, const double* __restrict__ x,
                                      double* __restrict__ x_old, int64_t n) {

@@ -76,8 +76,8 @@ class _handle:
         wx = np.ascontiguousarray(coef.Xh.wx)
         check(L.b200_adjrhs_set_space(self.h, dx.ctypes.data_as(C.POINTER(C.c_double)),
                                       wx.ctypes.data_as(C.POINTER(C.c_double))))
-        check(L.b200_adjrhs_set_geometry(self.h, *[_ptr(g) for g in coef.G], _ptr(coef.B)))
         check(L.b200_adjrhs_set_stream(self.h, _stream_ptr(stream)))
+        check(L.b200_adjrhs_set_geometry(self.h, *[_ptr(g) for g in coef.G], _ptr(coef.B)))
         self.n = coef.nelv * coef.Xh.lx ** 3
 
     def free(self):

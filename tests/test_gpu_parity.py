@@ -271,12 +271,14 @@ def test_full_size_properties():
     mk = lambda: [torch.empty(n, device="cuda", dtype=torch.float64) for _ in range(3)]
     a, b = 0.75, -1.5
     f1, f2, fm = mk(), mk(), mk()
+    op.set_params(if_lube=False)       # the lube term K*chi*u_b does not depend on the adjoint velocity
     op.compute(v1, ub, f1, rho=rho)
     op.compute(v2, ub, f2, rho=rho)
     op.compute([a * p + b * q for p, q in zip(v1, v2)], ub, fm, rho=rho)
     for c in range(3):
         ref = a * f1[c] + b * f2[c]
-        assert (torch.linalg.norm(fm[c] - ref) / torch.linalg.norm(ref)).item() <= 1e-12   # inputs a*v1+b*v2 are themselves rounded; D amplifies by ~lx^2
+        err = (torch.linalg.norm(fm[c] - ref) / torch.linalg.norm(ref)).item()
+        assert err <= 1e-11, f"linearity violated: {err:.3e}"   # a*v1+b*v2 is itself rounded; see below
     # determinism
     f1b = mk()
     op.compute(v1, ub, f1b, rho=rho)

@@ -20,6 +20,7 @@
 
 #include "adjrhs_kernel.cuh"
 #include "adjrhs_kernel_v2.cuh"
+#include "adjrhs_kernel_v3.cuh"
 #include "gs_kernels.cuh"
 #include "pointwise_kernels.cuh"
 
@@ -267,6 +268,81 @@ int launch_v2(Handle* h, const LaunchArgs& a) {
   return launch_v2_cfg<LX, NE, NS, NF_FUSED, MAXREG>(h, a);
 }
 
+// ---- third-generation kernel (adjrhs_kernel_v3.cuh): lx = 8, DMMA contractions --------------------------
+template <int NF>
+int fill_params2_lx8(Handle* h, const LaunchArgs& a, KParams2<8>& p) {
+  memset(&p, 0, sizeof p);
+  for (int i = 0; i < 64; i++) p.D[i] = h->D[i];
+  for (int i = 0; i < 8; i++) p.w[i] = h->w[i];
+  const size_t eoff = (size_t)a.elem_begin * 512;
+  for (int c = 0; c < 3; c++) p.ub[c] = a.vb[c] + eoff;
+  unsigned flags = 0;
+  if (!h->geom_pack) return fail(B200_ERR_STATE, "packed geometry image missing (set_geometry)");
+  p.geom = h->geom_pack + eoff * NGEO;
+  for (int c = 0; c < 3; c++) p.pf[R_V - NGEO + c] = a.v[c] + eoff;
+  if (a.sources) {
+    p.pf[R_RHO - NGEO] = a.rho + eoff;
+    flags |= FLAG_SOURCES;
+    if (!a.rho_is_chi) flags |= FLAG_RAMP;
+    if (h->convex_up) flags |= FLAG_CONVEX_UP;
+    if (h->if_lube && h->lube_mask_size == 0) flags |= FLAG_LUBE;
+    if (a.chi_out) flags |= FLAG_CHI_OUT;
+  }
+  if constexpr (NF >= NF_FULL) {
+    if (a.fs[0]) {
+      for (int c = 0; c < 3; c++) p.pf[R_FS - NGEO + c] = a.fs[c] + eoff;
+      flags |= FLAG_FSTATIC;
+    }
+    if (a.fin[0]) {
+      for (int c = 0; c < 3; c++) p.pf[R_FIN - NGEO + c] = a.fin[c] + eoff;
+      flags |= FLAG_ACCUM;
+    }
+  } else if (a.fs[0] || a.fin[0]) {
+    return fail(B200_ERR_STATE, "internal: static forcing / accumulate mode need the NF_FULL kernel");
+  }
+  if (a.sens) flags |= FLAG_SENS;
+  int na = NGEO;
+  for (int i = 0; i < NF_FULL - NGEO; i++) na += (p.pf[i] != nullptr);
+  p.n_active = na;
+  for (int c = 0; c < 3; c++) p.f[c] = a.f[c] + eoff;
+  p.sens = a.sens ? a.sens + eoff : nullptr;
+  p.chi_out = a.chi_out ? a.chi_out + eoff : nullptr;
+  p.elem_list = a.elem_list;
+  p.nelem = a.nelem;
+  p.flags = flags;
+  p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
+  p.K_sens = h->if_lube ? h->K_sens : 0.0;
+  return B200_OK;
+}
+
+template <int NE, int NW, int DS, int NF, int MAXREG>
+int launch_v3_cfg(Handle* h, const LaunchArgs& a) {
+  using C = V3Cfg<NE, NW, DS, NF>;
+  static_assert(C::SMEM <= 227 * 1024, "v3 configuration exceeds the shared memory of an SM");
+  static_assert(C::NTHREADS <= 1024, "v3 configuration exceeds 1024 threads");
+  static_assert(C::NTHREADS * MAXREG <= 65536, "v3 configuration exceeds the register file");
+  KParams2<8> p;
+  if (int r = fill_params2_lx8<NF>(h, a, p)) return r;
+  auto kern = adjrhs_v3_kernel<NE, NW, DS, NF, MAXREG>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  const int grid = std::min((a.nelem + NE - 1) / NE, h->num_sm);
+  if (grid < 1) return B200_OK;
+  kern<<<grid, C::NTHREADS, C::SMEM, h->stream>>>(p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+template <int NE, int NW, int DS, int MAXREG, int NE_FULL = NE, int DS_FULL = DS>
+int launch_v3(Handle* h, const LaunchArgs& a) {
+  if (a.fs[0] || a.fin[0]) return launch_v3_cfg<NE_FULL, NW, DS_FULL, NF_FULL, MAXREG>(h, a);
+  return launch_v3_cfg<NE, NW, DS, NF_FUSED, MAXREG>(h, a);
+}
+
 int launch_fused_v1(Handle* h, const LaunchArgs& a);
 
 int launch_fused(Handle* h, const LaunchArgs& a) {
@@ -288,7 +364,13 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
         case 6: return launch_v2<8, 3, 4, 224, 3, 4>(h, a);
         case 7: return launch_v2<8, 2, 4, 255, 2, 4>(h, a);
         case 8: return launch_v2<8, 2, 8, 255, 2, 4>(h, a);
-        default: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);
+        case 9: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);
+        case 20: return launch_v3<4, 4, 1, 128, 3, 1>(h, a); // 16 warps, 184 KB
+        case 21: return launch_v3<3, 4, 2, 168, 3, 1>(h, a); // 12 warps, 222 KB
+        case 22: return launch_v3<2, 8, 1, 128>(h, a);       // 16 warps, 1 plane per warp
+        case 23: return launch_v3<6, 2, 1, 168>(h, a);       // 12 warps, 4 planes per warp
+        case 25: return launch_v3<3, 4, 1, 168>(h, a);       // 12 warps, 138 KB
+        default: return launch_v3<3, 4, 2, 168, 3, 1>(h, a);
       }
     case 9: return launch_v2<9, 3, 2, 200>(h, a);
     case 10: return launch_v2<10, 2, 2, 224>(h, a);

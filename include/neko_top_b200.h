@@ -105,12 +105,36 @@ int b200_adv_adjoint_compute(void* handle,
                              const void* vx, const void* vy, const void* vz,
                              const void* vxb, const void* vyb, const void* vzb,
                              void* fx, void* fy, void* fz);
-/* advection_adjoint_t%compute_linear (adjoint/adv_adjoint_no_dealias.f90:365-427); needs jacinv. */
+/* advection_adjoint_t%compute_linear on the GLL grid (adjoint/adv_adjoint_no_dealias.f90:365-427):
+ * f_i -= B*jacinv*(U_b.grad u'_i + u'.grad U_b,i); f IN/OUT.  jacinv (coef%jacinv_d) is accepted for
+ * signature compatibility and may be NULL: B*jacinv == w3, which the kernel uses directly. */
 int b200_adv_linear_compute(void* handle,
                             const void* vx, const void* vy, const void* vz,
                             const void* vxb, const void* vyb, const void* vzb,
                             const void* jacinv,
                             void* fx, void* fy, void* fz);
+/* adv_lin_dealias_t%init (adjoint/adv_adjoint_dealias.f90:137-161).  HOST arrays of the fine
+ * Gauss-Legendre space: *lxd = Xh_GL%lx, interp = GLL_to_GL interpolation matrix (lxd x lx, column-major
+ * J(a,l)), dxd = Xh_GL%dx (lxd x lxd, column-major), wd = Xh_GL%wx (lxd).  Interpolates the nine
+ * geometric factors set by b200_adjrhs_set_geometry to the fine grid (coef_GL, :153-161) into
+ * library-owned memory (9*nelv*lxd^3*8 bytes).  Only lxd = 3*lx/2 -- the factory's default,
+ * adjoint/advection_adjoint_fctry.f90:70,89 -- is instantiated; anything else is an error. */
+int b200_adv_dealias_init(void* handle, const int* lxd, const double* interp, const double* dxd,
+                          const double* wd);
+/* adv_lin_dealias_t%compute_adjoint (adjoint/adv_adjoint_dealias.f90:235-462); f IN/OUT. */
+int b200_adv_adjoint_dealias_compute(void* handle,
+                                     const void* vx, const void* vy, const void* vz,
+                                     const void* vxb, const void* vyb, const void* vzb,
+                                     void* fx, void* fy, void* fz);
+/* adv_lin_dealias_t%compute_linear (adjoint/adv_adjoint_dealias.f90:479-668); f IN/OUT. */
+int b200_adv_linear_dealias_compute(void* handle,
+                                    const void* vx, const void* vy, const void* vz,
+                                    const void* vxb, const void* vyb, const void* vzb,
+                                    void* fx, void* fy, void* fz);
+/* *flag != 0: b200_adjrhs_compute / _step / _step_host evaluate the adjoint advection with the
+ * dealiased operator (case.numerics.dealias = true) instead of the GLL-grid one; needs
+ * b200_adv_dealias_init.  b200_adv_adjoint_compute always stays on the GLL grid. */
+int b200_adjrhs_set_dealias(void* handle, const int* flag);
 /* simple_brinkman_source_term_t%compute_ (source_terms/simple_brinkman_source_term.f90:139-153):
  * f_i -= chi*u_i */
 int b200_brinkman_compute(void* fu, void* fv, void* fw, const void* u, const void* v, const void* w,

@@ -15,7 +15,9 @@ SYMBOLS = [
     "b200_adjrhs_create", "b200_adjrhs_free", "b200_adjrhs_set_stream", "b200_adjrhs_set_space",
     "b200_adjrhs_set_geometry", "b200_adjrhs_set_params", "b200_adjrhs_set_lube_mask",
     "b200_adjrhs_compute", "b200_adjrhs_step", "b200_adjrhs_step_host",
-    "b200_adv_adjoint_compute", "b200_adv_linear_compute", "b200_brinkman_compute",
+    "b200_adv_adjoint_compute", "b200_adv_linear_compute", "b200_adv_dealias_init",
+    "b200_adv_adjoint_dealias_compute", "b200_adv_linear_dealias_compute", "b200_adjrhs_set_dealias",
+    "b200_brinkman_compute",
     "b200_lube_compute", "b200_opcolv", "b200_ramp_forward", "b200_ramp_backward",
     "b200_sensitivity", "b200_steady_field_update",
     "b200_gs_init", "b200_gs_get_classes", "b200_gs_op", "b200_gs_op3",
@@ -32,7 +34,7 @@ def build(force=False):
     if (not force and os.path.exists(SO_PATH)
             and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(s) for s in srcs)):
         return SO_PATH
-    subprocess.check_call(["make", "-B", "-C", csrc], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-j2", "-C", csrc], stdout=subprocess.DEVNULL)
     return SO_PATH
 
 

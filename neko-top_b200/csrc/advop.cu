@@ -1,0 +1,117 @@
+// Launchers of the fine-grid advection operators (advop_kernel.cuh).
+#include "advop.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "advop_kernel.cuh"
+
+namespace b200 {
+namespace {
+
+template <int LX, int LXD, int MODE>
+cudaError_t launch_one(const AdvLaunch& a) {
+  using C = AdvCfg<LX, LXD, MODE>;
+  static_assert(C::SMEM <= 227 * 1024, "fine-grid operator exceeds the shared memory of an SM");
+  // as many CTAs per SM as shared memory allows (+1 KB reserved per CTA); cap registers to match
+  constexpr int CTAS = (227 * 1024) / (C::SMEM + 1024) > 0 ? (227 * 1024) / (C::SMEM + 1024) : 1;
+  constexpr int RCAP = 65536 / (C::NTHR * CTAS) / 8 * 8;
+  constexpr int MAXREG = RCAP > 255 ? 255 : (RCAP < (C::NTHR <= 96 ? 224 : 168) ? (C::NTHR <= 96 ? 224 : 168) : RCAP);
+  AdvParams<LX, LXD> p;
+  memset(&p, 0, sizeof p);
+  for (int i = 0; i < LXD * LXD; i++) p.D[i] = a.D[i];
+  if (LXD != LX) for (int i = 0; i < LXD * LX; i++) p.J[i] = a.J[i];
+  for (int i = 0; i < LXD; i++) p.wd[i] = a.wd[i];
+  for (int c = 0; c < 3; c++) { p.v[c] = a.v[c]; p.vb[c] = a.vb[c]; p.f[c] = a.f[c]; p.fs[c] = a.fs[c]; }
+  for (int g = 0; g < 9; g++) p.G[g] = a.G[g];
+  p.rho = a.rho; p.B = a.B; p.sens = a.sens; p.chi_out = a.chi_out;
+  p.elem_list = a.elem_list; p.nelem = a.nelem; p.flags = a.flags;
+  p.f_min = a.f_min; p.f_max = a.f_max; p.q = a.q; p.K_lube = a.K_lube; p.K_sens = a.K_sens;
+  auto kern = advop_kernel<LX, LXD, MODE, MAXREG>;
+  static int per_sm = 0;   // per instantiation
+  if (!per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHR, C::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  }
+  const int grid = std::min(a.nelem, a.num_sm * per_sm);
+  if (grid < 1) return cudaSuccess;
+  kern<<<grid, C::NTHR, C::SMEM, a.stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int LX>
+cudaError_t launch_lx(const AdvLaunch& a, const char** msg) {
+  constexpr int LXD = 3 * LX / 2;
+  if (a.lxd == LX) {
+    if (a.mode == ADV_LINEAR) return launch_one<LX, LX, ADV_LINEAR>(a);
+    *msg = "the GLL-grid adjoint operator is the fused element kernel, not the fine-grid one";
+    return cudaErrorInvalidValue;
+  }
+  if (a.lxd != LXD) {
+    *msg = "dealiased operator: only lxd = 3*lx/2 (the factory default, advection_adjoint_fctry.f90:70) is instantiated";
+    return cudaErrorInvalidValue;
+  }
+  if (a.mode == ADV_ADJOINT) return launch_one<LX, LXD, ADV_ADJOINT>(a);
+  return launch_one<LX, LXD, ADV_LINEAR>(a);
+}
+
+template <int LX>
+cudaError_t geom_lx(int lxd, const double* J_host, const double* const src[9], double* const dst[9],
+                    int nelv, int num_sm, cudaStream_t stream, const char** msg) {
+  constexpr int LXD = 3 * LX / 2;
+  if (lxd != LXD) {
+    *msg = "dealiased operator: only lxd = 3*lx/2 is instantiated";
+    return cudaErrorInvalidValue;
+  }
+  GeomInterpParams<LX, LXD> p;
+  for (int i = 0; i < LXD * LX; i++) p.J[i] = J_host[i];
+  for (int g = 0; g < 9; g++) { p.src[g] = src[g]; p.dst[g] = dst[g]; }
+  p.nelv = nelv;
+  constexpr int NTHR = ((LXD * LXD + 31) / 32) * 32;
+  constexpr int SMEM = (LX * LX * LX + LXD * LX * LX + LXD * LXD * LX + LXD * LX) * 8;
+  auto kern = geom_to_fine_kernel<LX, LXD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  if (e != cudaSuccess) return e;
+  const long long total = 9ll * nelv;
+  const int grid = (int)std::min<long long>(total, (long long)num_sm * 8);
+  if (grid < 1) return cudaSuccess;
+  kern<<<grid, NTHR, SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t advop_launch(const AdvLaunch& a, const char** msg) {
+  *msg = nullptr;
+  switch (a.lx) {
+    case 4: return launch_lx<4>(a, msg);
+    case 5: return launch_lx<5>(a, msg);
+    case 6: return launch_lx<6>(a, msg);
+    case 7: return launch_lx<7>(a, msg);
+    case 8: return launch_lx<8>(a, msg);
+    case 9: return launch_lx<9>(a, msg);
+    case 10: return launch_lx<10>(a, msg);
+    default: *msg = "lx not instantiated (4..10)"; return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t advop_geom_to_fine(int lx, int lxd, const double* J_host, const double* const src[9],
+                               double* const dst[9], int nelv, int num_sm, cudaStream_t stream,
+                               const char** msg) {
+  *msg = nullptr;
+  switch (lx) {
+    case 4: return geom_lx<4>(lxd, J_host, src, dst, nelv, num_sm, stream, msg);
+    case 5: return geom_lx<5>(lxd, J_host, src, dst, nelv, num_sm, stream, msg);
+    case 6: return geom_lx<6>(lxd, J_host, src, dst, nelv, num_sm, stream, msg);
+    case 7: return geom_lx<7>(lxd, J_host, src, dst, nelv, num_sm, stream, msg);
+    case 8: return geom_lx<8>(lxd, J_host, src, dst, nelv, num_sm, stream, msg);
+    case 9: return geom_lx<9>(lxd, J_host, src, dst, nelv, num_sm, stream, msg);
+    case 10: return geom_lx<10>(lxd, J_host, src, dst, nelv, num_sm, stream, msg);
+    default: *msg = "lx not instantiated (4..10)"; return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace b200

@@ -21,6 +21,7 @@
 #include "adjrhs_kernel.cuh"
 #include "adjrhs_kernel_v2.cuh"
 #include "adjrhs_kernel_v3.cuh"
+#include "advop.h"
 #include "gs_kernels.cuh"
 #include "pointwise_kernels.cuh"
 
@@ -78,6 +79,12 @@ struct Handle {
   const int* lube_mask = nullptr;
   int lube_mask_size = 0;
   int cfg = -1;   // kernel configuration override (B200_ADJRHS_CFG)
+
+  // dealiased operator: the state of adv_lin_dealias_t (adjoint/adv_adjoint_dealias.f90:56-131)
+  int lxd = 0;                     // 0: b200_adv_dealias_init not called
+  bool dealias_fused = false;      // b200_adjrhs_compute/step use the dealiased operator
+  std::vector<double> Jd, Dd, wd;  // GLL_to_GL matrix (lxd x lx), Xh_GL%dx, Xh_GL%wx
+  double* G_fine = nullptr;        // coef_GL: 9 arrays of nelv*lxd^3 (one allocation)
 
   // gather-scatter
   bool have_gs = false;
@@ -139,6 +146,7 @@ struct LaunchArgs {
   int nelem;
   int elem_begin;         // used only when elem_list == nullptr (via pointer offsets)
   bool sources;
+  bool no_dealias;         // un-fused GLL-grid drop-in: ignore the handle's dealias switch
 };
 
 template <int LX, int PC, int NS, int NU, int MAXREG>
@@ -345,8 +353,54 @@ int launch_v3(Handle* h, const LaunchArgs& a) {
 
 int launch_fused_v1(Handle* h, const LaunchArgs& a);
 
+// fine-grid operators (advop_kernel.cuh): dealiased adjoint / linearised advection, GLL-grid linearised
+int launch_fine(Handle* h, const LaunchArgs& a, int mode, bool dealias) {
+  if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
+  if (dealias && h->lxd == 0) return fail(B200_ERR_STATE, "b200_adv_dealias_init not called");
+  AdvLaunch L;
+  memset(&L, 0, sizeof L);
+  L.lx = h->lx; L.mode = mode;
+  const size_t nd = dealias ? (size_t)h->nelv * h->lxd * h->lxd * h->lxd : (size_t)h->n;
+  if (dealias) {
+    L.lxd = h->lxd; L.D = h->Dd.data(); L.J = h->Jd.data(); L.wd = h->wd.data();
+    for (int g = 0; g < 9; g++) L.G[g] = h->G_fine + g * nd;
+  } else {
+    L.lxd = h->lx; L.D = h->D; L.J = nullptr; L.wd = h->w;
+    for (int g = 0; g < 9; g++) L.G[g] = h->G[g];
+  }
+  unsigned flags = 0;
+  for (int c = 0; c < 3; c++) { L.v[c] = a.v[c]; L.vb[c] = a.vb[c]; L.f[c] = a.f[c]; L.fs[c] = a.fs[c]; }
+  if (a.fin[0]) {
+    flags |= FLAG_ACCUM;     // advection_adjoint_t contract: f in/out
+  } else {
+    if (a.sources) {
+      L.rho = a.rho;
+      flags |= FLAG_SOURCES;
+      if (!a.rho_is_chi) flags |= FLAG_RAMP;
+      if (h->convex_up) flags |= FLAG_CONVEX_UP;
+      if (h->if_lube && h->lube_mask_size == 0) flags |= FLAG_LUBE;
+      if (a.chi_out) flags |= FLAG_CHI_OUT;
+    }
+    if (a.fs[0]) flags |= FLAG_FSTATIC;
+    if (a.sens) flags |= FLAG_SENS;
+  }
+  L.B = h->B; L.sens = a.sens; L.chi_out = a.chi_out;
+  L.elem_list = a.elem_list; L.nelem = a.nelem; L.flags = flags;
+  L.f_min = h->f_min; L.f_max = h->f_max; L.q = h->q; L.K_lube = h->K_lube;
+  L.K_sens = h->if_lube ? h->K_sens : 0.0;
+  L.num_sm = h->num_sm; L.stream = h->stream;
+  const char* msg = nullptr;
+  cudaError_t e = advop_launch(L, &msg);
+  if (e != cudaSuccess)
+    return fail(msg ? B200_ERR_ARG : B200_ERR_CUDA, "fine-grid advection operator (lx=%d lxd=%d mode=%d): %s",
+                L.lx, L.lxd, mode, msg ? msg : cudaGetErrorString(e));
+  if (a.nelem > 0) LAUNCHED();
+  return B200_OK;
+}
+
 int launch_fused(Handle* h, const LaunchArgs& a) {
   if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
+  if (h->dealias_fused && !a.no_dealias) return launch_fine(h, a, ADV_ADJOINT, true);
   const int cfg = h->cfg;
   if (cfg >= 100) return launch_fused_v1(h, a);
   switch (h->lx) {
@@ -498,6 +552,7 @@ LaunchArgs make_args(const void* vx, const void* vy, const void* vz, const void*
   a.elem_list = nullptr;
   a.nelem = nelv;
   a.elem_begin = 0;
+  a.no_dealias = false;
   return a;
 }
 
@@ -559,7 +614,7 @@ int b200_adjrhs_free(void** handle) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep); cudaFree(h->gs_skip);
-  cudaFree(h->gs_shared_cls); cudaFree(h->geom_pack);
+  cudaFree(h->gs_shared_cls); cudaFree(h->geom_pack); cudaFree(h->G_fine);
   cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
   cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_bnd_elem);
   cudaFree(h->d_int_elem);
@@ -731,12 +786,84 @@ int b200_adv_adjoint_compute(void* handle, const void* vx, const void* vy, const
   LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, nullptr, nullptr, nullptr, nullptr, nullptr, fx, fy,
                            fz, nullptr, nullptr, h->nelv);
   a.fin[0] = (const double*)fx; a.fin[1] = (const double*)fy; a.fin[2] = (const double*)fz;
+  a.no_dealias = true;
   return launch_fused(h, a);
 }
 
-int b200_adv_linear_compute(void*, const void*, const void*, const void*, const void*, const void*,
-                            const void*, const void*, void*, void*, void*) {
-  return fail(B200_ERR_STATE, "compute_linear is a SURVEY.md 8(f) 'next' row; not built yet");
+int b200_adv_linear_compute(void* handle, const void* vx, const void* vy, const void* vz,
+                            const void* vxb, const void* vyb, const void* vzb, const void* jacinv,
+                            void* fx, void* fy, void* fz) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!vx || !vy || !vz || !vxb || !vyb || !vzb || !fx || !fy || !fz)
+    return fail(B200_ERR_ARG, "adv_linear_compute: null pointer");
+  (void)jacinv;   // B*jacinv == w3 (coef%B = jac*w3): the kernel uses the quadrature weights directly
+  CK(cudaSetDevice(h->device));
+  LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, nullptr, nullptr, nullptr, nullptr, nullptr, fx, fy,
+                           fz, nullptr, nullptr, h->nelv);
+  a.fin[0] = (const double*)fx; a.fin[1] = (const double*)fy; a.fin[2] = (const double*)fz;
+  return launch_fine(h, a, ADV_LINEAR, false);
+}
+
+int b200_adv_dealias_init(void* handle, const int* lxd, const double* interp, const double* dxd,
+                          const double* wd) {
+  if (!handle || !lxd || !interp || !dxd || !wd) return fail(B200_ERR_ARG, "adv_dealias_init: null argument");
+  Handle* h = H(handle);
+  if (!h->have_geom) return fail(B200_ERR_STATE, "adv_dealias_init: call b200_adjrhs_set_geometry first");
+  const int ld = *lxd;
+  if (ld != advop_default_lxd(h->lx))
+    return fail(B200_ERR_ARG, "adv_dealias_init: lxd=%d, only 3*lx/2=%d is instantiated for lx=%d "
+                "(advection_adjoint_fctry.f90:70,89)", ld, advop_default_lxd(h->lx), h->lx);
+  CK(cudaSetDevice(h->device));
+  h->Jd.assign(interp, interp + (size_t)ld * h->lx);
+  h->Dd.assign(dxd, dxd + (size_t)ld * ld);
+  h->wd.assign(wd, wd + ld);
+  const size_t nd = (size_t)h->nelv * ld * ld * ld;
+  if (h->G_fine) { CK(cudaFree(h->G_fine)); h->G_fine = nullptr; }
+  CK(cudaMalloc(&h->G_fine, sizeof(double) * 9 * std::max<size_t>(nd, 1)));
+  double* dst[9];
+  for (int g = 0; g < 9; g++) dst[g] = h->G_fine + g * nd;
+  const char* msg = nullptr;
+  cudaError_t e = advop_geom_to_fine(h->lx, ld, h->Jd.data(), h->G, dst, h->nelv, h->num_sm, h->stream, &msg);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "adv_dealias_init: %s", msg ? msg : cudaGetErrorString(e));
+  if (h->nelv > 0) LAUNCHED();
+  CK(cudaStreamSynchronize(h->stream));
+  h->lxd = ld;
+  return B200_OK;
+}
+
+int b200_adjrhs_set_dealias(void* handle, const int* flag) {
+  if (!handle || !flag) return fail(B200_ERR_ARG, "set_dealias: null argument");
+  Handle* h = H(handle);
+  if (*flag && h->lxd == 0) return fail(B200_ERR_STATE, "set_dealias: b200_adv_dealias_init not called");
+  h->dealias_fused = (*flag != 0);
+  return B200_OK;
+}
+
+static int adv_dealias_compute(void* handle, int mode, const void* vx, const void* vy, const void* vz,
+                               const void* vxb, const void* vyb, const void* vzb, void* fx, void* fy,
+                               void* fz) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!vx || !vy || !vz || !vxb || !vyb || !vzb || !fx || !fy || !fz)
+    return fail(B200_ERR_ARG, "adv dealias compute: null pointer");
+  CK(cudaSetDevice(h->device));
+  LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, nullptr, nullptr, nullptr, nullptr, nullptr, fx, fy,
+                           fz, nullptr, nullptr, h->nelv);
+  a.fin[0] = (const double*)fx; a.fin[1] = (const double*)fy; a.fin[2] = (const double*)fz;
+  return launch_fine(h, a, mode, true);
+}
+
+int b200_adv_adjoint_dealias_compute(void* handle, const void* vx, const void* vy, const void* vz,
+                                     const void* vxb, const void* vyb, const void* vzb, void* fx, void* fy,
+                                     void* fz) {
+  return adv_dealias_compute(handle, ADV_ADJOINT, vx, vy, vz, vxb, vyb, vzb, fx, fy, fz);
+}
+
+int b200_adv_linear_dealias_compute(void* handle, const void* vx, const void* vy, const void* vz,
+                                    const void* vxb, const void* vyb, const void* vzb, void* fx, void* fy,
+                                    void* fz) {
+  return adv_dealias_compute(handle, ADV_LINEAR, vx, vy, vz, vxb, vyb, vzb, fx, fy, fz);
 }
 
 // ---- un-fused point-wise drop-ins -------------------------------------------------------------

@@ -19,7 +19,8 @@ module adv_lin_b200
   use, intrinsic :: iso_c_binding
   use num_types, only : rp
   use advection_adjoint, only : advection_adjoint_t
-  use space, only : space_t
+  use space, only : space_t, GL
+  use interpolation, only : interpolator_t
   use field, only : field_t
   use coefs, only : coef_t
   use neko_config, only : NEKO_BCKND_DEVICE
@@ -44,7 +45,73 @@ module adv_lin_b200
      procedure, pass(this) :: free => free_b200
   end type adv_lin_b200_t
 
+  !> Dealiased variant: replaces `adv_lin_dealias_t`
+  !! (adjoint/adv_adjoint_dealias.f90:56-131).  The fine Gauss-Legendre space
+  !! and the GLL->GL interpolator are built exactly as `init_dealias` does
+  !! (:143-146); the library interpolates the geometric factors (coef_GL,
+  !! :153-161) and owns all fine-grid storage, so none of the 20 work arrays
+  !! of :166-208 exist here.
+  type, public, extends(adv_lin_b200_t) :: adv_lin_dealias_b200_t
+     type(space_t) :: Xh_GL
+     type(interpolator_t) :: GLL_to_GL
+   contains
+     procedure, pass(this) :: compute_linear => linear_advection_dealias_b200
+     procedure, pass(this) :: compute_adjoint => adjoint_advection_dealias_b200
+     procedure, pass(this) :: init_dealias => init_dealias_b200
+  end type adv_lin_dealias_b200_t
+
 contains
+
+  !> Constructor; same arguments as `init_dealias`
+  !! (adjoint/adv_adjoint_dealias.f90:137-161).
+  !! @param lxd  number of Gauss-Legendre points; must be 3*lx/2
+  !! @param coef The coefficients of the (space, mesh) pair.
+  subroutine init_dealias_b200(this, lxd, coef)
+    class(adv_lin_dealias_b200_t), intent(inout) :: this
+    integer, intent(in) :: lxd
+    type(coef_t), intent(inout), target :: coef
+    integer(c_int) :: ierr, lxd_c
+
+    call this%adv_lin_b200_t%init(coef)
+    call this%Xh_GL%init(GL, lxd, lxd, lxd)
+    call this%GLL_to_GL%init(this%Xh_GL, coef%Xh)
+    lxd_c = lxd
+    ! GLL_to_GL%Xh_to_Yh is the (lxd x lx) interpolation matrix J(a,l)
+    ierr = b200_adv_dealias_init(this%handle, lxd_c, &
+         this%GLL_to_GL%Xh_to_Yh, this%Xh_GL%dx, this%Xh_GL%wx)
+  end subroutine init_dealias_b200
+
+  !> Same argument list as `compute_adjoint_advection_dealias`; `f` in/out.
+  subroutine adjoint_advection_dealias_b200(this, vx, vy, vz, vxb, vyb, vzb, &
+       fx, fy, fz, Xh, coef, n)
+    class(adv_lin_dealias_b200_t), intent(inout) :: this
+    type(space_t), intent(inout) :: Xh
+    type(coef_t), intent(inout) :: coef
+    type(field_t), intent(inout) :: vx, vy, vz
+    type(field_t), intent(inout) :: vxb, vyb, vzb
+    type(field_t), intent(inout) :: fx, fy, fz
+    integer, intent(in) :: n
+    integer(c_int) :: ierr
+
+    ierr = b200_adv_adjoint_dealias_compute(this%handle, vx%x_d, vy%x_d, &
+         vz%x_d, vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d)
+  end subroutine adjoint_advection_dealias_b200
+
+  !> Same argument list as `compute_linear_advection_dealias`; `f` in/out.
+  subroutine linear_advection_dealias_b200(this, vx, vy, vz, vxb, vyb, vzb, &
+       fx, fy, fz, Xh, coef, n)
+    class(adv_lin_dealias_b200_t), intent(inout) :: this
+    type(space_t), intent(inout) :: Xh
+    type(coef_t), intent(inout) :: coef
+    type(field_t), intent(inout) :: vx, vy, vz
+    type(field_t), intent(inout) :: vxb, vyb, vzb
+    type(field_t), intent(inout) :: fx, fy, fz
+    integer, intent(in) :: n
+    integer(c_int) :: ierr
+
+    ierr = b200_adv_linear_dealias_compute(this%handle, vx%x_d, vy%x_d, &
+         vz%x_d, vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d)
+  end subroutine linear_advection_dealias_b200
 
   !> Constructor; same argument as `init_no_dealias`.
   !! @param coef The coefficients of the (space, mesh) pair.

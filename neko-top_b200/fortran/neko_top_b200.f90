@@ -138,6 +138,39 @@ module neko_top_b200
        type(c_ptr), value :: fx_d, fy_d, fz_d
      end function b200_adv_linear_compute
 
+     integer(c_int) function b200_adv_dealias_init(handle, lxd, interp, dxd, wd) &
+          bind(c, name='b200_adv_dealias_init')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       integer(c_int) :: lxd
+       real(c_double), dimension(*) :: interp, dxd, wd
+     end function b200_adv_dealias_init
+
+     integer(c_int) function b200_adv_adjoint_dealias_compute(handle, vx_d, &
+          vy_d, vz_d, vxb_d, vyb_d, vzb_d, fx_d, fy_d, fz_d) &
+          bind(c, name='b200_adv_adjoint_dealias_compute')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: vx_d, vy_d, vz_d, vxb_d, vyb_d, vzb_d
+       type(c_ptr), value :: fx_d, fy_d, fz_d
+     end function b200_adv_adjoint_dealias_compute
+
+     integer(c_int) function b200_adv_linear_dealias_compute(handle, vx_d, &
+          vy_d, vz_d, vxb_d, vyb_d, vzb_d, fx_d, fy_d, fz_d) &
+          bind(c, name='b200_adv_linear_dealias_compute')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: vx_d, vy_d, vz_d, vxb_d, vyb_d, vzb_d
+       type(c_ptr), value :: fx_d, fy_d, fz_d
+     end function b200_adv_linear_dealias_compute
+
+     integer(c_int) function b200_adjrhs_set_dealias(handle, flag) &
+          bind(c, name='b200_adjrhs_set_dealias')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       integer(c_int) :: flag
+     end function b200_adjrhs_set_dealias
+
      integer(c_int) function b200_brinkman_compute(fu_d, fv_d, fw_d, u_d, &
           v_d, w_d, chi_d, n, stream) bind(c, name='b200_brinkman_compute')
        use, intrinsic :: iso_c_binding

@@ -80,6 +80,19 @@ class _handle:
         check(L.b200_adjrhs_set_geometry(self.h, *[_ptr(g) for g in coef.G], _ptr(coef.B)))
         self.n = coef.nelv * coef.Xh.lx ** 3
 
+    def dealias_init(self, lxd=None):
+        """adv_lin_dealias_t%init (adjoint/adv_adjoint_dealias.f90:137-161): hand the fine GL space and
+        the GLL_to_GL matrix to the library, which interpolates the geometric factors (coef_GL)."""
+        from . import sem
+        if getattr(self, "lxd", 0) and (lxd is None or lxd == self.lxd):
+            return
+        ds = sem.DealiasSpace(self.coef.Xh.lx, lxd)
+        dp = C.POINTER(C.c_double)
+        J, Dd, wd = ds.interp_colmajor, ds.dxd_colmajor, np.ascontiguousarray(ds.wd)
+        check(_lib.lib().b200_adv_dealias_init(self.h, _ci(ds.lxd), J.ctypes.data_as(dp), Dd.ctypes.data_as(dp),
+                                               wd.ctypes.data_as(dp)))
+        self.lxd = ds.lxd
+
     def free(self):
         if self.h:
             check(_lib.lib().b200_adjrhs_free(C.byref(self.h)))
@@ -133,6 +146,34 @@ class adv_lin_b200_t(advection_adjoint_t):
             self._hd = None
 
 
+class adv_lin_dealias_b200_t(advection_adjoint_t):
+    """B200 replacement of adv_lin_dealias_t (adjoint/adv_adjoint_dealias.f90:56-131)."""
+
+    def __init__(self):
+        self._hd = None
+
+    def init(self, lxd, coef, handle=None):
+        self._hd = handle if handle is not None else _handle(coef)
+        self._hd.dealias_init(lxd)
+
+    def compute_adjoint(self, vx, vy, vz, vxb, vyb, vzb, fx, fy, fz, Xh=None, coef=None, n=None):
+        """adjoint/adv_adjoint_dealias.f90:235-462; f_i IN/OUT."""
+        if n is not None and n != self._hd.n:
+            raise ValueError(f"n={n} does not match the handle ({self._hd.n})")
+        check(_lib.lib().b200_adv_adjoint_dealias_compute(self._hd.h, _ptr(vx), _ptr(vy), _ptr(vz), _ptr(vxb),
+                                                          _ptr(vyb), _ptr(vzb), _ptr(fx), _ptr(fy), _ptr(fz)))
+
+    def compute_linear(self, vx, vy, vz, vxb, vyb, vzb, fx, fy, fz, Xh=None, coef=None, n=None):
+        """adjoint/adv_adjoint_dealias.f90:479-668; f_i IN/OUT."""
+        check(_lib.lib().b200_adv_linear_dealias_compute(self._hd.h, _ptr(vx), _ptr(vy), _ptr(vz), _ptr(vxb),
+                                                         _ptr(vyb), _ptr(vzb), _ptr(fx), _ptr(fy), _ptr(fz)))
+
+    def free(self):
+        if self._hd is not None:
+            self._hd.free()
+            self._hd = None
+
+
 def advection_adjoint_factory(json, coef, handle=None):
     """adjoint/advection_adjoint_fctry.f90:57-96.  `json` is a dict with the case keys
     case.numerics.{dealias, polynomial_order, dealiased_polynomial_order}; one extra key,
@@ -140,7 +181,14 @@ def advection_adjoint_factory(json, coef, handle=None):
     num = json.get("case", {}).get("numerics", {})
     dealias = bool(num.get("dealias", False))
     if dealias:
-        raise NotImplementedError("dealiased B200 operator is a later SURVEY.md section-8 row (a4)")
+        lxd = num.get("dealiased_polynomial_order")
+        if lxd is None:
+            lxd = 3 * (int(num["polynomial_order"]) + 1) // 2       # :67-71 "assumes odd polynomial order"
+        if lxd <= 0:
+            lxd = coef.Xh.lx * 3 // 2                               # :89
+        obj = adv_lin_dealias_b200_t()
+        obj.init(lxd, coef, handle)
+        return obj
     obj = adv_lin_b200_t()
     obj.init(coef, handle)
     return obj
@@ -289,6 +337,12 @@ class fused_adjoint_rhs_t:
     def set_params(self, f_min=0.0, f_max=1000.0, q=1.0, convex_up=True, if_lube=True, K_lube=1.0, K_sens=1.0):
         check(_lib.lib().b200_adjrhs_set_params(self._hd.h, _cd(f_min), _cd(f_max), _cd(q), _ci(convex_up),
                                                 _ci(if_lube), _cd(K_lube), _cd(K_sens)))
+
+    def set_dealias(self, flag=True, lxd=None):
+        """compute()/step() use the dealiased adjoint operator (case.numerics.dealias = true)."""
+        if flag:
+            self._hd.dealias_init(lxd)
+        check(_lib.lib().b200_adjrhs_set_dealias(self._hd.h, _ci(bool(flag))))
 
     def set_lube_mask(self, mask):
         self._mask = mask

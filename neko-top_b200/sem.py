@@ -129,6 +129,28 @@ class Space:
         return np.einsum("k,j,i->kji", self.wx, self.wx, self.wx)
 
 
+class DealiasSpace:
+    """What adv_lin_dealias_t%init builds (adjoint/adv_adjoint_dealias.f90:137-146): the fine
+    Gauss-Legendre space Xh_GL (lxd points: nodes, weights, derivative matrix) and the GLL -> GL
+    interpolation matrix of GLL_to_GL.  Default lxd = 3*lx/2 (advection_adjoint_fctry.f90:70,89)."""
+
+    def __init__(self, lx, lxd=None):
+        self.lx = lx
+        self.lxd = 3 * lx // 2 if lxd is None else int(lxd)
+        zg, _ = zwgll(lx)
+        self.zd, self.wd = zwgl(self.lxd)
+        self.interp = interp_matrix(self.zd, zg)        # [a, l] = J(a, l)
+        self.dxd = deriv_matrix(self.zd)                # [i, j] = D(i, j)
+
+    @property
+    def interp_colmajor(self):
+        return np.ascontiguousarray(self.interp.T).reshape(-1)
+
+    @property
+    def dxd_colmajor(self):
+        return np.ascontiguousarray(self.dxd.T).reshape(-1)
+
+
 def geometric_factors(x, y, z, space, chunk=32768):
     """coef_t arrays for nodal coordinates x,y,z of shape (nelv, lx, lx, lx) [e,k,j,i] (torch, any
     device).  Returns (G, jac, B): G = [drdx,dsdx,dtdx, drdy,dsdy,dtdy, drdz,dsdz,dtdz]."""
@@ -184,5 +206,5 @@ def algorithmic_flops_per_dof(lx):
     return 36.0 * lx + 136.0
 
 
-__all__ = ["zwgll", "zwgl", "dgll", "deriv_matrix", "interp_matrix", "Space", "geometric_factors",
+__all__ = ["zwgll", "zwgl", "dgll", "deriv_matrix", "interp_matrix", "Space", "DealiasSpace", "geometric_factors",
            "phi_surface", "algorithmic_bytes_per_dof", "algorithmic_flops_per_dof", "math"]

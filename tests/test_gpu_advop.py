@@ -1,0 +1,169 @@
+"""GPU parity of the fine-grid advection operators against the CPU
+oracle: dealiased adjoint operator, linearised operator with and without dealiasing, the factory rule,
+the fused right-hand side with dealiasing, and the discrete adjoint identity evaluated on the GPU.
+fp64 fields: relative L2 <= 1e-12 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import Problem, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _ops():
+    from neko_top_b200 import operators
+    return operators
+
+
+def _coef(P, with_jacinv=False):
+    ops = _ops()
+    jacinv = (1.0 / P.t["jac"]).reshape(-1).cuda().contiguous() if with_jacinv else None
+    return ops.coef_t(ops.space_t(P.lx, P.D, P.w), P.nelv, P.cuda("G"), P.cuda("B"), jacinv)
+
+
+def _case(lx, dealias):
+    return {"case": {"numerics": {"dealias": dealias, "polynomial_order": lx - 1}}}
+
+
+def _nan(n):
+    return torch.full((n,), float("nan"), device="cuda", dtype=torch.float64)
+
+
+@pytest.mark.parametrize("lx", [4, 5, 6, 7, 8, 9, 10])
+def test_dealiased_adjoint_plugin(oracle, lx):
+    """adv_lin_dealias_t%compute_adjoint (adv_adjoint_dealias.f90:235-462); f in/out; lxd = 3*lx/2."""
+    ops = _ops()
+    P = Problem(lx, ne=(2, 2, 3) if lx < 9 else (2, 2, 1), deform=0.03)
+    lxd = 3 * lx // 2
+    rng = np.random.default_rng(11)
+    f0 = [rng.standard_normal(P.n) for _ in range(3)]
+    fo = oracle.adjoint_advection_dealias(f0, P.v, P.ub, lx, lxd, P.nelv, P.G)
+    adv = ops.advection_adjoint_factory(_case(lx, True), _coef(P))
+    assert isinstance(adv, ops.adv_lin_dealias_b200_t)
+    f = [torch.as_tensor(a).cuda() for a in f0]
+    adv.compute_adjoint(*P.cuda("v"), *P.cuda("ub"), *f, n=P.n)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL, f"f[{c}] lx={lx}"
+    adv.free()
+
+
+@pytest.mark.parametrize("lx", [4, 5, 6, 7, 8, 9, 10])
+def test_linear_plugin_no_dealias(oracle, lx):
+    """adv_lin_no_dealias_t%compute_linear (adv_adjoint_no_dealias.f90:365-427); f in/out."""
+    ops = _ops()
+    P = Problem(lx, ne=(2, 3, 2), deform=0.03)
+    rng = np.random.default_rng(12)
+    f0 = [rng.standard_normal(P.n) for _ in range(3)]
+    fo = oracle.linear_advection_no_dealias(f0, P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.jac)
+    adv = ops.advection_adjoint_factory(_case(lx, False), _coef(P, with_jacinv=True))
+    assert isinstance(adv, ops.adv_lin_b200_t)
+    f = [torch.as_tensor(a).cuda() for a in f0]
+    adv.compute_linear(*P.cuda("v"), *P.cuda("ub"), *f, n=P.n)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL, f"f[{c}] lx={lx}"
+    adv.free()
+
+
+@pytest.mark.parametrize("lx", [4, 5, 6, 7, 8, 9, 10])
+def test_linear_plugin_dealias(oracle, lx):
+    """adv_lin_dealias_t%compute_linear (adv_adjoint_dealias.f90:479-668); f in/out."""
+    ops = _ops()
+    P = Problem(lx, ne=(2, 2, 2) if lx < 9 else (2, 1, 1), deform=0.03)
+    lxd = 3 * lx // 2
+    rng = np.random.default_rng(13)
+    f0 = [rng.standard_normal(P.n) for _ in range(3)]
+    fo = oracle.linear_advection_dealias(f0, P.v, P.ub, lx, lxd, P.nelv, P.G)
+    adv = ops.advection_adjoint_factory(_case(lx, True), _coef(P))
+    f = [torch.as_tensor(a).cuda() for a in f0]
+    adv.compute_linear(*P.cuda("v"), *P.cuda("ub"), *f, n=P.n)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL, f"f[{c}] lx={lx}"
+    adv.free()
+
+
+def test_factory_rule_and_errors():
+    """advection_adjoint_fctry.f90:65-91: lxd from dealiased_polynomial_order, else 3*(order+1)/2; a
+    fine order that is not instantiated fails loudly (no fallback)."""
+    ops = _ops()
+    from neko_top_b200 import _lib
+    P = Problem(6, ne=(1, 1, 2), deform=0.0)
+    coef = _coef(P)
+    adv = ops.advection_adjoint_factory({"case": {"numerics": {"dealias": True, "polynomial_order": 5,
+                                                               "dealiased_polynomial_order": 9}}}, coef)
+    assert adv._hd.lxd == 9
+    adv.free()
+    _lib.set_abort_on_error(0)
+    try:
+        with pytest.raises(_lib.B200Error):
+            ops.advection_adjoint_factory({"case": {"numerics": {"dealias": True, "polynomial_order": 5,
+                                                                 "dealiased_polynomial_order": 11}}}, coef)
+        op = ops.fused_adjoint_rhs_t(coef)
+        with pytest.raises(_lib.B200Error):      # set_dealias before dealias_init
+            _lib.check(_lib.lib().b200_adjrhs_set_dealias(op.handle.h, ops._ci(1)))
+        op.free()
+    finally:
+        _lib.set_abort_on_error(1)
+
+
+@pytest.mark.parametrize("lx", [6, 8])
+def test_fused_rhs_dealias(oracle, lx):
+    """case.numerics.dealias = true in the fused path: sources + mass matrix + DEALIASED adjoint advection
+    + sensitivity (+ gs) against orc_adjoint_rhs with lxd > 0; BASELINE configs[2] runs this variant."""
+    P = Problem(lx, ne=(3, 2, 2), deform=0.03)
+    lxd = 3 * lx // 2
+    ops = _ops()
+    op = ops.fused_adjoint_rhs_t(_coef(P))
+    op.set_dealias(True)
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    fo, so, co = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho, lxd=lxd)
+    f, sens, chi = [_nan(P.n) for _ in range(3)], _nan(P.n), _nan(P.n)
+    op.compute(v, ub, f, rho=rho, sens=sens, chi_out=chi)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    assert np.array_equal(chi.cpu().numpy(), co)
+    # static forcing + given chi, then the whole step with gs
+    rng = np.random.default_rng(3)
+    chi_in = rng.random(P.n) * 1000.0
+    fs = [rng.standard_normal(P.n) for _ in range(3)]
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, chi=chi_in, fstatic=fs, lxd=lxd)
+    cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
+    op.gs.init(P.keys.reshape(-1).cuda())
+    f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+    op.step(v, ub, f, chi=torch.as_tensor(chi_in).cuda(), fstatic=[torch.as_tensor(a).cuda() for a in fs], sens=sens)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), oracle.gs_add(fo[c], cid, nc)) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    # switching back gives the GLL-grid operator again
+    op.set_dealias(False)
+    fo, _, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    f = [_nan(P.n) for _ in range(3)]
+    op.compute(v, ub, f, rho=rho)
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    op.free()
+
+
+@pytest.mark.parametrize("dealias", [False, True])
+def test_discrete_adjoint_identity_gpu(dealias):
+    """<w, L v> == <A w, v> with L = compute_linear and A = compute_adjoint evaluated by the CUDA kernels on
+    a deformed (non-affine) mesh: |diff| / (|w| |L v|) <= 1e-12 (SURVEY.md 8d correctness gates)."""
+    ops = _ops()
+    lx = 7
+    P = Problem(lx, ne=(2, 2, 2), deform=0.05)
+    Q = Problem(lx, ne=(2, 2, 2), deform=0.05, seed_shift=777)
+    adv = ops.advection_adjoint_factory(_case(lx, dealias), _coef(P, with_jacinv=True))
+    ub = P.cuda("ub")
+    v, w = P.cuda("v"), Q.cuda("v")
+    z = lambda: [torch.zeros(P.n, device="cuda", dtype=torch.float64) for _ in range(3)]
+    Lv, Aw = z(), z()
+    adv.compute_linear(*v, *ub, *Lv, n=P.n)
+    adv.compute_adjoint(*w, *ub, *Aw, n=P.n)
+    lhs = sum((a * b).sum().item() for a, b in zip(w, Lv))
+    rhs = sum((a * b).sum().item() for a, b in zip(Aw, v))
+    nw = np.sqrt(sum((a * a).sum().item() for a in w))
+    nl = np.sqrt(sum((a * a).sum().item() for a in Lv))
+    assert nl > 0 and abs(lhs - rhs) / (nw * nl) <= 1e-12
+    adv.free()

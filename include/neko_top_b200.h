@@ -187,6 +187,20 @@ int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof,
 /* elements that own a shared node (computed first so the exchange overlaps the interior ones) */
 int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* bnd_elem);
 
+/* Processing order of the elements in the fused step (a permutation of 0..nelv-1, HOST; *nelem = 0
+ * restores 0..nelv-1).  Results do not depend on it; speed does: b200_adjrhs_step sums the node classes
+ * inside the element kernel as soon as all their member elements are stored, which only pays while the
+ * earlier members are still in L2 -- neighbouring elements should be close in this order (for a structured
+ * box: columns of 16x16 elements; bench.py / workloads.tile_order).  Neko's mesh order is arbitrary, so
+ * the order is an input, exactly like the partition. */
+int b200_adjrhs_set_element_order(void* handle, const int* nelem, const int* order);
+/* *flag = 0: b200_adjrhs_step keeps the separate gather-scatter pass (default 1; environment
+ * B200_GS_FUSED=0 does the same at create time).  Both paths give bit-identical results. */
+int b200_adjrhs_set_gs_fused(void* handle, const int* flag);
+/* *fused = 1 if b200_adjrhs_step currently sums node classes inside the element kernel;
+ * *classes_in_kernel of *classes_total are handled there (the rest: shared-node path, > 16 members). */
+int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, int64_t* classes_total);
+
 /* ---- diagnostics ----------------------------------------------------------------------------*/
 /* average device time (ms) of the last fused element-kernel launches measured with CUDA events
  * on the handle's stream when profiling is enabled; used by bench.py's roofline block */

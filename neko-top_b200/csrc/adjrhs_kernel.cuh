@@ -49,7 +49,9 @@ enum : unsigned {
   FLAG_SENS = 32u,
   FLAG_CHI_OUT = 64u,
   FLAG_CONVEX_UP = 128u,
-  FLAG_LINEAR = 256u     // (reserved)
+  FLAG_LINEAR = 256u,    // (reserved)
+  FLAG_GS = 512u,        // v3 kernel: direct-stiffness summation inside the element kernel
+  FLAG_L2HINT = 1024u    // v3 kernel: L2 evict_first policy on the streaming inputs / sens / chi
 };
 
 template <int LX>
@@ -105,6 +107,24 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
           smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+// same with an L2 eviction-priority hint (createpolicy handle)
+__device__ __forceinline__ void tma_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_f64x2_hint(double* addr, double a, double b, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(addr), "d"(a), "d"(b), "l"(policy)
+               : "memory");
 }
 // 8-byte Ampere-style async copy (SASS: LDGSTS) + deferred arrive, for odd LX
 __device__ __forceinline__ void cp_async_8(void* dst, const void* src) {

@@ -109,6 +109,24 @@ struct Handle {
   int *d_bnd_elem = nullptr, *d_int_elem = nullptr;
   int nbnd = 0, nint = 0;
 
+  // in-kernel direct-stiffness summation (adjrhs_kernel_v3.cuh FLAG_GS): element processing order and the
+  // class schedule built for it by build_gs_schedule()
+  std::vector<int> order;          // processing order of the elements (empty: 0..nelv-1)
+  int* d_order = nullptr;
+  int gs_mode = 0;                 // 0: CSR kernels (default, fastest), 1: packed class lists, 2: inside the v3 element kernel
+  int gs_lag = 2;                  // B200_GS_LAG
+  int gs_un = 1;                   // classes in flight per thread in gs_op_kernel (B200_GS_UN: 1, 2, 4; measured: 1 is best)
+  bool gs_l2hint = true;           // B200_GS_L2HINT=0: no evict_first policy on the streaming inputs
+  bool sched_valid = false;
+  int sched_nelem = 0;             // length of the element list the schedule was built for
+  int sched_kind = 0;              // 1: all elements (single GPU), 2: interior elements (multi-GPU split)
+  int *sched_eoff = nullptr, *sched_pair = nullptr, *sched_quad = nullptr, *sched_oct = nullptr,
+      *sched_hex = nullptr, *sched_left = nullptr;
+  int sched_nleft = 0;
+  int sched_n2 = 0, sched_n4 = 0, sched_n8 = 0, sched_n16 = 0;
+  int64_t sched_nfused = 0;        // classes summed inside the element kernel
+  unsigned long long* sched_done = nullptr;
+
   // host-staged step
   double* stage[11] = {};
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -147,6 +165,7 @@ struct LaunchArgs {
   int elem_begin;         // used only when elem_list == nullptr (via pointer offsets)
   bool sources;
   bool no_dealias;         // un-fused GLL-grid drop-in: ignore the handle's dealias switch
+  bool gs_in_kernel;       // sum the node classes inside the element kernel (needs a valid schedule)
 };
 
 template <int LX, int PC, int NS, int NU, int MAXREG>
@@ -320,18 +339,40 @@ int fill_params2_lx8(Handle* h, const LaunchArgs& a, KParams2<8>& p) {
   p.flags = flags;
   p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
   p.K_sens = h->if_lube ? h->K_sens : 0.0;
+  if (a.gs_in_kernel) {
+    if (!h->sched_valid || a.elem_begin != 0 || a.nelem != h->sched_nelem)
+      return fail(B200_ERR_STATE, "internal: in-kernel gs without a matching schedule");
+    p.flags |= FLAG_GS;
+    p.gs_eoff = reinterpret_cast<const int4*>(h->sched_eoff);
+    p.gs_pair = reinterpret_cast<const int2*>(h->sched_pair);
+    p.gs_quad = reinterpret_cast<const int4*>(h->sched_quad);
+    p.gs_oct = reinterpret_cast<const int4*>(h->sched_oct);
+    p.gs_hex = reinterpret_cast<const int4*>(h->sched_hex);
+    p.gs_done = h->sched_done;
+    p.gs_lag = h->gs_lag;
+  }
   return B200_OK;
 }
 
-template <int NE, int NW, int DS, int NF, int MAXREG>
+template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST>
+int launch_v3_cfg2(Handle* h, const LaunchArgs& a);
+
+template <int NE, int NW, int DS, int NF, int MAXREG, bool GS = false, bool HINT = false>
 int launch_v3_cfg(Handle* h, const LaunchArgs& a) {
+  if (a.elem_list) return launch_v3_cfg2<NE, NW, DS, NF, MAXREG, GS, HINT, true>(h, a);
+  return launch_v3_cfg2<NE, NW, DS, NF, MAXREG, GS, HINT, false>(h, a);
+}
+
+template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST>
+int launch_v3_cfg2(Handle* h, const LaunchArgs& a) {
   using C = V3Cfg<NE, NW, DS, NF>;
+  if (a.gs_in_kernel != GS) return fail(B200_ERR_STATE, "internal: v3 kernel variant / gs_in_kernel mismatch");
   static_assert(C::SMEM <= 227 * 1024, "v3 configuration exceeds the shared memory of an SM");
   static_assert(C::NTHREADS <= 1024, "v3 configuration exceeds 1024 threads");
   static_assert(C::NTHREADS * MAXREG <= 65536, "v3 configuration exceeds the register file");
   KParams2<8> p;
   if (int r = fill_params2_lx8<NF>(h, a, p)) return r;
-  auto kern = adjrhs_v3_kernel<NE, NW, DS, NF, MAXREG>;
+  auto kern = adjrhs_v3_kernel<NE, NW, DS, NF, MAXREG, GS, HINT, LIST>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -339,6 +380,14 @@ int launch_v3_cfg(Handle* h, const LaunchArgs& a) {
   }
   const int grid = std::min((a.nelem + NE - 1) / NE, h->num_sm);
   if (grid < 1) return B200_OK;
+  if (a.gs_in_kernel) {
+    // one completion counter per window of grid*NE positions; the spin-wait needs every CTA resident
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHREADS, C::SMEM));
+    if (per_sm < 1) return fail(B200_ERR_STATE, "v3 kernel does not fit on an SM");
+    const int nwin = (a.nelem + grid * NE - 1) / (grid * NE);
+    CK(cudaMemsetAsync(h->sched_done, 0, sizeof(unsigned long long) * nwin, h->stream));
+  }
   kern<<<grid, C::NTHREADS, C::SMEM, h->stream>>>(p);
   LAUNCHED();
   CK(cudaGetLastError());
@@ -347,8 +396,23 @@ int launch_v3_cfg(Handle* h, const LaunchArgs& a) {
 
 template <int NE, int NW, int DS, int MAXREG, int NE_FULL = NE, int DS_FULL = DS>
 int launch_v3(Handle* h, const LaunchArgs& a) {
+  if (a.gs_in_kernel) return fail(B200_ERR_STATE, "internal: this v3 configuration has no in-kernel gs variant");
   if (a.fs[0] || a.fin[0]) return launch_v3_cfg<NE_FULL, NW, DS_FULL, NF_FULL, MAXREG>(h, a);
   return launch_v3_cfg<NE, NW, DS, NF_FUSED, MAXREG>(h, a);
+}
+// the default configuration: also built with the in-kernel direct-stiffness summation
+int launch_v3_default(Handle* h, const LaunchArgs& a) {
+  const bool full = a.fs[0] || a.fin[0];
+  if (!a.gs_in_kernel) {
+    if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168>(h, a);
+    return launch_v3_cfg<3, 4, 2, NF_FUSED, 168>(h, a);
+  }
+  if (h->gs_l2hint) {
+    if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168, true, true>(h, a);
+    return launch_v3_cfg<3, 4, 2, NF_FUSED, 168, true, true>(h, a);
+  }
+  if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168, true, false>(h, a);
+  return launch_v3_cfg<3, 4, 2, NF_FUSED, 168, true, false>(h, a);
 }
 
 int launch_fused_v1(Handle* h, const LaunchArgs& a);
@@ -424,7 +488,7 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
         case 22: return launch_v3<2, 8, 1, 128>(h, a);       // 16 warps, 1 plane per warp
         case 23: return launch_v3<6, 2, 1, 168>(h, a);       // 12 warps, 4 planes per warp
         case 25: return launch_v3<3, 4, 1, 168>(h, a);       // 12 warps, 138 KB
-        default: return launch_v3<3, 4, 2, 168, 3, 1>(h, a);
+        default: return launch_v3_default(h, a);
       }
     case 9: return launch_v2<9, 3, 2, 200>(h, a);
     case 10: return launch_v2<10, 2, 2, 224>(h, a);
@@ -483,7 +547,9 @@ int gs_launch(Handle* h, double* f0, double* f1, double* f2, int nf) {
   const int threads = 256;
   const int grid = grid_for(h->nclass, threads, h->num_sm, 8);
   if (nf == 1) gs_op_kernel<1><<<grid, threads, 0, h->stream>>>(f0, f0, f0, h->gs_off, h->gs_dof, h->nclass);
-  else gs_op_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass);
+  else if (h->gs_un == 1) gs_op_kernel<3, 1><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass);
+  else if (h->gs_un == 4) gs_op_kernel<3, 4><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass);
+  else gs_op_kernel<3, 2><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass);
   LAUNCHED();
   CK(cudaGetLastError());
   return B200_OK;
@@ -534,6 +600,121 @@ int dmalloc(T** p, size_t count) {
   return B200_OK;
 }
 
+// true if launch_fused() will run the v3 element kernel (the one that can sum node classes itself)
+bool uses_v3(const Handle* h) {
+  return h->lx == 8 && !h->dealias_fused && (h->cfg <= 0 || (h->cfg > 25 && h->cfg < 100));   // default config
+}
+
+void free_schedule(Handle* h) {
+  cudaFree(h->sched_eoff); cudaFree(h->sched_pair); cudaFree(h->sched_quad); cudaFree(h->sched_oct);
+  cudaFree(h->sched_hex); cudaFree(h->sched_left); cudaFree(h->sched_done);
+  h->sched_eoff = h->sched_pair = h->sched_quad = h->sched_oct = h->sched_hex = h->sched_left = nullptr;
+  h->sched_done = nullptr;
+  h->sched_valid = false; h->sched_nleft = 0; h->sched_nfused = 0; h->sched_nelem = 0; h->sched_kind = 0;
+}
+
+// Class schedule of the in-kernel direct-stiffness summation for the element list (list, nlist)
+// (list == nullptr: elements 0..nlist-1 in order).  Elements outside the list count as already stored.
+int build_gs_schedule(Handle* h, const int* list, int nlist) {
+  free_schedule(h);
+  if (!h->have_gs || h->nclass == 0 || nlist == 0) return B200_OK;
+  cudaStream_t st = h->stream;
+  const int nc = h->nclass, threads = 256;
+  int *d_pos = nullptr, *d_cls = nullptr, *d_cls2 = nullptr, *d_bstart = nullptr;
+  unsigned long long *d_key = nullptr, *d_key2 = nullptr;
+  if (int r = dmalloc(&d_pos, (size_t)h->nelv)) return r;
+  if (int r = dmalloc(&d_cls, (size_t)nc)) return r;
+  if (int r = dmalloc(&d_cls2, (size_t)nc)) return r;
+  if (int r = dmalloc(&d_key, (size_t)nc)) return r;
+  if (int r = dmalloc(&d_key2, (size_t)nc)) return r;
+  if (int r = dmalloc(&d_bstart, 8)) return r;
+  CK(cudaMemsetAsync(d_pos, 0xff, sizeof(int) * (size_t)h->nelv, st));
+  gs_pos_kernel<<<grid_for(nlist, threads, h->num_sm, 8), threads, 0, st>>>(list, nlist, d_pos);
+  LAUNCHED();
+  gs_class_key_kernel<<<grid_for(nc, threads, h->num_sm, 8), threads, 0, st>>>(
+      h->gs_off, h->gs_dof, h->gs_skip, nc, d_pos, h->lx * h->lx * h->lx, d_key, d_cls);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_cls, d_cls2, nc, 0, 44, st));
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_cls, d_cls2, nc, 0, 44, st));
+  CK(cudaFree(d_tmp));
+  if (int r = dmalloc(&h->sched_eoff, 4 * ((size_t)nlist + 1))) return r;
+  gs_eoff_kernel<<<grid_for(4ll * (nlist + 1) + 7, threads, h->num_sm, 8), threads, 0, st>>>(
+      d_key2, nc, nlist, h->sched_eoff, d_bstart);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  int bstart[8] = {};
+  CK(cudaMemcpyAsync(bstart, d_bstart, sizeof(int) * 7, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const size_t n2 = bstart[1] - bstart[0], n4 = bstart[2] - bstart[1], n8 = bstart[3] - bstart[2],
+               n16 = bstart[4] - bstart[3], nl = bstart[5] - bstart[4];
+  if (int r = dmalloc(&h->sched_pair, 2 * n2 + 4)) return r;
+  if (int r = dmalloc(&h->sched_quad, 4 * n4 + 4)) return r;
+  if (int r = dmalloc(&h->sched_oct, 8 * n8 + 4)) return r;
+  if (int r = dmalloc(&h->sched_hex, 16 * n16 + 4)) return r;
+  if (int r = dmalloc(&h->sched_left, nl + 1)) return r;
+  if (bstart[5] > 0) {
+    gs_fill_kernel<<<grid_for(bstart[5], threads, h->num_sm, 8), threads, 0, st>>>(
+        d_cls2, d_bstart, h->gs_off, h->gs_dof, h->sched_pair, h->sched_quad, h->sched_oct, h->sched_hex,
+        h->sched_left);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
+  if (int r = dmalloc(&h->sched_done, (size_t)nlist + 1)) return r;
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(d_pos)); CK(cudaFree(d_cls)); CK(cudaFree(d_cls2)); CK(cudaFree(d_key)); CK(cudaFree(d_key2));
+  CK(cudaFree(d_bstart));
+  h->sched_nleft = (int)nl;
+  h->sched_n2 = (int)n2; h->sched_n4 = (int)n4; h->sched_n8 = (int)n8; h->sched_n16 = (int)n16;
+  h->sched_nfused = (int64_t)(n2 + n4 + n8 + n16);
+  h->sched_nelem = nlist;
+  h->sched_valid = true;
+  return B200_OK;
+}
+
+// separate gather-scatter pass over the packed lists of the schedule (3 fields)
+int gs_packed(Handle* h, double* f0, double* f1, double* f2) {
+  const int threads = 256;
+  if (h->sched_n2 > 0) {
+    constexpr int UN = 4;
+    const int grid = grid_for((h->sched_n2 + UN - 1) / UN, threads, h->num_sm, 8);
+    gs_pairs_kernel<UN><<<grid, threads, 0, h->stream>>>(f0, f1, f2, reinterpret_cast<const int2*>(h->sched_pair),
+                                                         h->sched_n2);
+    LAUNCHED();
+  }
+  if (h->sched_n4 > 0) {
+    gs_wide_kernel<4><<<grid_for(h->sched_n4, threads, h->num_sm, 8), threads, 0, h->stream>>>(
+        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_quad), h->sched_n4);
+    LAUNCHED();
+  }
+  if (h->sched_n8 > 0) {
+    gs_wide_kernel<8><<<grid_for(h->sched_n8, threads, h->num_sm, 8), threads, 0, h->stream>>>(
+        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_oct), h->sched_n8);
+    LAUNCHED();
+  }
+  if (h->sched_n16 > 0) {
+    gs_wide_kernel<16><<<grid_for(h->sched_n16, threads, h->num_sm, 4), threads, 0, h->stream>>>(
+        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_hex), h->sched_n16);
+    LAUNCHED();
+  }
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+// classes with more than 16 members are not in the in-kernel schedule
+int gs_leftover(Handle* h, double* f0, double* f1, double* f2) {
+  if (h->sched_nleft == 0) return B200_OK;
+  const int threads = 256, grid = grid_for(h->sched_nleft, threads, h->num_sm, 4);
+  gs_op_list_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->sched_left,
+                                                         h->sched_nleft);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
 LaunchArgs make_args(const void* vx, const void* vy, const void* vz, const void* vxb, const void* vyb,
                      const void* vzb, const void* rho, const void* chi_in, const void* fsx,
                      const void* fsy, const void* fsz, void* fx, void* fy, void* fz, void* sens,
@@ -553,6 +734,7 @@ LaunchArgs make_args(const void* vx, const void* vy, const void* vz, const void*
   a.nelem = nelv;
   a.elem_begin = 0;
   a.no_dealias = false;
+  a.gs_in_kernel = false;
   return a;
 }
 
@@ -604,6 +786,16 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   h->num_sm = prop.multiProcessorCount;
   const char* c = getenv("B200_ADJRHS_CFG");
   h->cfg = c ? atoi(c) : -1;
+  const char* g = getenv("B200_GS_FUSED");
+  if (g) h->gs_mode = atoi(g) != 0 ? 2 : 1;
+  g = getenv("B200_GS_MODE");
+  if (g) h->gs_mode = std::min(2, std::max(0, atoi(g)));
+  g = getenv("B200_GS_UN");
+  if (g) h->gs_un = atoi(g);
+  g = getenv("B200_GS_LAG");
+  if (g) h->gs_lag = std::max(1, atoi(g));
+  g = getenv("B200_GS_L2HINT");
+  if (g) h->gs_l2hint = atoi(g) != 0;
   *handle = h;
   return B200_OK;
 }
@@ -615,6 +807,7 @@ int b200_adjrhs_free(void** handle) {
   cudaDeviceSynchronize();
   cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep); cudaFree(h->gs_skip);
   cudaFree(h->gs_shared_cls); cudaFree(h->geom_pack); cudaFree(h->G_fine);
+  free_schedule(h); cudaFree(h->d_order);
   cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
   cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_bnd_elem);
   cudaFree(h->d_int_elem);
@@ -738,10 +931,30 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
   double *f0 = a.f[0], *f1 = a.f[1], *f2 = a.f[2];
   if (int r = time_mark(h)) return r;
   const bool split = h->comm && h->nshared > 0 && h->nbnd > 0 && h->n_shared_cls >= 0 && h->gs_skip;
+  // direct-stiffness summation inside the element kernel (v3, lx = 8) while f is still in L2; the masked
+  // lube term is applied by a separate kernel after the element kernel, so it keeps the separate gs pass
+  const bool masked_lube = a.sources && h->if_lube && h->lube_mask_size > 0;
+  // gs_mode 2: summation inside the v3 element kernel; 1: separate pass over the packed class lists of the
+  // schedule; 0: the CSR kernels.  Without a boundary/interior split a communicator needs the CSR pass
+  // (it sums the shared classes too, before the exchange).
+  int mode = h->gs_mode;
+  if (h->nclass == 0 || (!split && h->comm && h->nshared > 0)) mode = 0;
+  if (mode == 2 && (!uses_v3(h) || masked_lube || (split && h->nint == 0))) mode = 1;
+  if (mode > 0) {
+    const int kind = split ? 2 : 1;
+    if (!h->sched_valid || h->sched_kind != kind) {
+      if (int r = build_gs_schedule(h, split ? h->d_int_elem : h->d_order, split ? h->nint : h->nelv)) return r;
+      h->sched_kind = kind;
+    }
+    if (!h->sched_valid) mode = 0;
+  }
+  const bool fuse_gs = (mode == 2);
   if (split) {
     // boundary elements first, their shared nodes summed locally, packed and sent while the interior
     // elements are computed
-    LaunchArgs ab = a; ab.elem_list = h->d_bnd_elem; ab.nelem = h->nbnd;
+    // (with a masked lube term the point-zone kernel must see every element before any summation: no overlap)
+    LaunchArgs ab = a;
+    if (!masked_lube) { ab.elem_list = h->d_bnd_elem; ab.nelem = h->nbnd; }
     if (int r = launch_fused(h, ab)) return r;
     if (int r = masked_lube_post(h, a)) return r;
     if (h->n_shared_cls > 0) {
@@ -752,10 +965,15 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
       CK(cudaGetLastError());
     }
     if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
-    LaunchArgs ai = a; ai.elem_list = h->d_int_elem; ai.nelem = h->nint;
-    if (h->nint > 0) if (int r = launch_fused(h, ai)) return r;
+    LaunchArgs ai = a; ai.elem_list = h->d_int_elem; ai.nelem = h->nint; ai.gs_in_kernel = fuse_gs;
+    if (h->nint > 0 && !masked_lube) if (int r = launch_fused(h, ai)) return r;
     if (int r = time_mark(h)) return r;
-    if (h->nclass > 0) {
+    if (mode == 2) {
+      if (int r = gs_leftover(h, f0, f1, f2)) return r;
+    } else if (mode == 1) {
+      if (int r = gs_packed(h, f0, f1, f2)) return r;
+      if (int r = gs_leftover(h, f0, f1, f2)) return r;
+    } else if (h->nclass > 0) {
       const int threads = 256, grid = grid_for(h->nclass, threads, h->num_sm, 8);
       gs_op_skip_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->gs_skip,
                                                              h->nclass);
@@ -764,14 +982,65 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     }
     if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
   } else {
+    a.elem_list = h->d_order; a.gs_in_kernel = fuse_gs;
     if (int r = launch_fused(h, a)) return r;
     if (int r = masked_lube_post(h, a)) return r;
     if (int r = time_mark(h)) return r;
-    if (int r = gs_launch(h, f0, f1, f2, 3)) return r;
-    if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
-    if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
+    if (mode == 2) {
+      if (int r = gs_leftover(h, f0, f1, f2)) return r;
+    } else if (mode == 1) {
+      if (int r = gs_packed(h, f0, f1, f2)) return r;
+      if (int r = gs_leftover(h, f0, f1, f2)) return r;
+    } else {
+      if (int r = gs_launch(h, f0, f1, f2, 3)) return r;
+      if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
+      if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
+    }
   }
   return time_mark(h);
+}
+
+int b200_adjrhs_set_element_order(void* handle, const int* nelem, const int* order) {
+  if (!handle || !nelem) return fail(B200_ERR_ARG, "set_element_order: null argument");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  free_schedule(h);
+  cudaFree(h->d_order); h->d_order = nullptr;
+  h->order.clear();
+  if (*nelem == 0 || !order) return B200_OK;     // back to 0..nelv-1
+  if (*nelem != h->nelv) return fail(B200_ERR_ARG, "set_element_order: %d entries, nelv = %d", *nelem, h->nelv);
+  std::vector<char> seen(h->nelv, 0);
+  for (int i = 0; i < h->nelv; i++) {
+    const int e = order[i];
+    if (e < 0 || e >= h->nelv || seen[e]) return fail(B200_ERR_ARG, "set_element_order: not a permutation");
+    seen[e] = 1;
+  }
+  h->order.assign(order, order + h->nelv);
+  if (int r = dmalloc(&h->d_order, (size_t)h->nelv)) return r;
+  CK(cudaMemcpy(h->d_order, order, sizeof(int) * (size_t)h->nelv, cudaMemcpyHostToDevice));
+  if (h->nbnd > 0 && h->d_bnd_elem) {            // keep the interior list in the new order
+    std::vector<int> bnd(h->nbnd);
+    CK(cudaMemcpy(bnd.data(), h->d_bnd_elem, sizeof(int) * (size_t)h->nbnd, cudaMemcpyDeviceToHost));
+    const int nb = h->nbnd;
+    return b200_adjrhs_set_boundary_elements(handle, &nb, bnd.data());
+  }
+  return B200_OK;
+}
+
+int b200_adjrhs_set_gs_fused(void* handle, const int* flag) {
+  if (!handle || !flag) return fail(B200_ERR_ARG, "set_gs_fused: null argument");
+  H(handle)->gs_mode = (*flag > 0) ? 2 : (*flag < 0 ? 0 : 1);
+  return B200_OK;
+}
+
+int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, int64_t* classes_total) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (fused) *fused = (h->sched_valid && h->gs_mode == 2) ? 1 : 0;
+  if (classes_in_kernel) *classes_in_kernel = h->sched_valid ? h->sched_nfused : 0;
+  if (classes_total) *classes_total = h->nclass;
+  return B200_OK;
 }
 
 int b200_adv_adjoint_compute(void* handle, const void* vx, const void* vy, const void* vz,
@@ -991,6 +1260,7 @@ int b200_gs_init(void* handle, const int64_t* key, const int* on_device) {
   cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep);
   h->gs_off = h->gs_dof = h->gs_rep = nullptr;
   h->have_gs = false;
+  free_schedule(h);
   if (n == 0) { h->nclass = 0; h->nmember = 0; h->have_gs = true; return B200_OK; }
 
   int64_t *d_key_in = nullptr, *d_key = nullptr, *d_comp = nullptr, *d_comp2 = nullptr;
@@ -1174,6 +1444,7 @@ int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof,
   CK(cudaSetDevice(h->device));
   const int ns = *nshared, nn = *nneigh;
   h->nshared = ns; h->nneigh = nn;
+  free_schedule(h);
   cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
   cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->gs_skip);
   cudaFree(h->gs_shared_cls);
@@ -1251,6 +1522,7 @@ int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* 
   cudaFree(h->d_bnd_elem); cudaFree(h->d_int_elem);
   h->d_bnd_elem = h->d_int_elem = nullptr;
   h->nbnd = *nbnd; h->nint = 0;
+  free_schedule(h);
   if (*nbnd == 0) return B200_OK;
   if (!bnd_elem) return fail(B200_ERR_ARG, "set_boundary_elements: null list");
   std::vector<char> isb(h->nelv, 0);
@@ -1259,7 +1531,10 @@ int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* 
     isb[bnd_elem[i]] = 1;
   }
   std::vector<int> bnd, inte;
-  for (int e = 0; e < h->nelv; e++) (isb[e] ? bnd : inte).push_back(e);
+  for (int i = 0; i < h->nelv; i++) {            // interior elements keep the processing order
+    const int e = h->order.empty() ? i : h->order[i];
+    (isb[e] ? bnd : inte).push_back(e);
+  }
   h->nbnd = (int)bnd.size(); h->nint = (int)inte.size();
   if (int r = dmalloc(&h->d_bnd_elem, bnd.size())) return r;
   if (int r = dmalloc(&h->d_int_elem, inte.size())) return r;

@@ -65,22 +65,55 @@ __global__ void gs_classid_kernel(const int* __restrict__ rep, const int* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cid[i] = scan[rep[i]];
 }
 
-template <int NF>
+// UN classes per thread are in flight together (every class has >= 2 members, so the first two members of
+// each are gathered unconditionally; the rare longer classes finish in a loop): the pass is bound by the
+// latency of the chain offsets -> members -> values, not by bandwidth.
+template <int NF, int UN = 2>
 __global__ void gs_op_kernel(double* f0, double* f1, double* f2,
                              const int* __restrict__ off, const int* __restrict__ dof, int nclass) {
   const int stride = gridDim.x * blockDim.x;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
-    const int b = off[c], e = off[c + 1];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int m = b; m < e; m++) {
-      const int d = dof[m];
-      s0 += f0[d];
-      if (NF > 1) { s1 += f1[d]; s2 += f2[d]; }
+  for (int c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < nclass; c0 += stride * UN) {
+    int b[UN], e[UN], d0[UN], d1[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const int c = c0 + u * stride;
+      b[u] = e[u] = 0;
+      if (c < nclass) { b[u] = off[c]; e[u] = off[c + 1]; }
     }
-    for (int m = b; m < e; m++) {
-      const int d = dof[m];
-      f0[d] = s0;
-      if (NF > 1) { f1[d] = s1; f2[d] = s2; }
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      d0[u] = d1[u] = 0;
+      if (e[u] > b[u]) { d0[u] = dof[b[u]]; d1[u] = dof[b[u] + 1]; }
+    }
+    double s[UN][3];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      if (e[u] > b[u]) {
+        const double a0 = f0[d0[u]], c0v = f0[d1[u]];
+        s[u][0] = (0.0 + a0) + c0v;
+        if (NF > 1) {
+          const double a1 = f1[d0[u]], c1v = f1[d1[u]], a2 = f2[d0[u]], c2v = f2[d1[u]];
+          s[u][1] = (0.0 + a1) + c1v;
+          s[u][2] = (0.0 + a2) + c2v;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      if (e[u] > b[u]) {
+        for (int m = b[u] + 2; m < e[u]; m++) {
+          const int d = dof[m];
+          s[u][0] += f0[d];
+          if (NF > 1) { s[u][1] += f1[d]; s[u][2] += f2[d]; }
+        }
+        f0[d0[u]] = s[u][0]; f0[d1[u]] = s[u][0];
+        if (NF > 1) { f1[d0[u]] = s[u][1]; f1[d1[u]] = s[u][1]; f2[d0[u]] = s[u][2]; f2[d1[u]] = s[u][2]; }
+        for (int m = b[u] + 2; m < e[u]; m++) {
+          const int d = dof[m];
+          f0[d] = s[u][0];
+          if (NF > 1) { f1[d] = s[u][1]; f2[d] = s[u][2]; }
+        }
+      }
     }
   }
 }
@@ -201,6 +234,141 @@ __global__ void gs_op_skip_kernel(double* f0, double* f1, double* f2,
       f0[d] = s0;
       if (NF > 1) { f1[d] = s1; f2[d] = s2; }
     }
+  }
+}
+
+// ---- schedule of the in-kernel direct-stiffness summation (adjrhs_kernel_v3.cuh, FLAG_GS) ------------------
+// pos[e] = position of element e in the processing list (-1: not in the list == stored before the launch)
+__global__ void gs_pos_kernel(const int* __restrict__ order, int norder, int* __restrict__ pos) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < norder; i += stride) pos[order ? order[i] : i] = i;
+}
+// sort key of a class: (bucket << 40) | completing position.  bucket 0: 2 members, 1: 3-4, 2: 5-8, 3: 9-16,
+// 4: more (left to gs_op_list_kernel), 5: handled by the multi-GPU shared-node path (skip).
+__global__ void gs_class_key_kernel(const int* __restrict__ off, const int* __restrict__ dof,
+                                    const unsigned char* __restrict__ skip, int nclass,
+                                    const int* __restrict__ pos, int npts, unsigned long long* __restrict__ key,
+                                    int* __restrict__ cls) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
+    const int b = off[c], e = off[c + 1], deg = e - b;
+    int bucket = deg <= 2 ? 0 : deg <= 4 ? 1 : deg <= 8 ? 2 : deg <= 16 ? 3 : 4;
+    if (skip && skip[c]) bucket = 5;
+    int pm = 0;
+    for (int m = b; m < e; m++) pm = max(pm, pos[dof[m] / npts]);
+    key[c] = ((unsigned long long)bucket << 40) | (unsigned long long)pm;
+    cls[c] = c;
+  }
+}
+__device__ __forceinline__ int gs_lower_bound(const unsigned long long* __restrict__ a, int n,
+                                              unsigned long long v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// bstart[b] = first sorted index of bucket b (b = 0..6); eoff[p*4 + b] = first entry of position p in the
+// list of bucket b (p = 0..nelem)
+__global__ void gs_eoff_kernel(const unsigned long long* __restrict__ key, int nclass, int nelem,
+                               int* __restrict__ eoff, int* __restrict__ bstart) {
+  const long long total = 4ll * (nelem + 1);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total + 7; w += stride) {
+    if (w >= total) {
+      const int b = (int)(w - total);
+      bstart[b] = gs_lower_bound(key, nclass, (unsigned long long)b << 40);
+      continue;
+    }
+    const int b = (int)(w & 3);
+    const long long p = w >> 2;
+    const unsigned long long base = (unsigned long long)b << 40;
+    eoff[w] = gs_lower_bound(key, nclass, base | (unsigned long long)p) - gs_lower_bound(key, nclass, base);
+  }
+}
+// packed member lists, -1 padded; left[] = class ids of bucket 4
+__global__ void gs_fill_kernel(const int* __restrict__ cls, const int* __restrict__ bstart,
+                               const int* __restrict__ off, const int* __restrict__ dof,
+                               int* __restrict__ pair, int* __restrict__ quad, int* __restrict__ oct,
+                               int* __restrict__ hex, int* __restrict__ left) {
+  const int stride = gridDim.x * blockDim.x;
+  const int nfill = bstart[5];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nfill; i += stride) {
+    const int c = cls[i];
+    const int b = off[c], deg = off[c + 1] - b;
+    if (i >= bstart[4]) { left[i - bstart[4]] = c; continue; }
+    int* dst; int width;
+    if (i < bstart[1]) { dst = pair + 2 * (size_t)(i - bstart[0]); width = 2; }
+    else if (i < bstart[2]) { dst = quad + 4 * (size_t)(i - bstart[1]); width = 4; }
+    else if (i < bstart[3]) { dst = oct + 8 * (size_t)(i - bstart[2]); width = 8; }
+    else { dst = hex + 16 * (size_t)(i - bstart[3]); width = 16; }
+    for (int m = 0; m < width; m++) dst[m] = m < deg ? dof[b + m] : -1;
+  }
+}
+
+// ---- separate pass over the packed lists of the schedule -------------------------------------------------
+// pairs (most classes): UN independent classes per thread -> 6*UN gathers in flight per thread; the class
+// descriptor is one coalesced int2 load (no offset/member indirection as in gs_op_kernel).
+template <int UN>
+__global__ void __launch_bounds__(256) gs_pairs_kernel(double* __restrict__ f0, double* __restrict__ f1,
+                                                      double* __restrict__ f2, const int2* __restrict__ pair,
+                                                      int npair) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < npair; base += stride * UN) {
+    int2 q[UN];
+    bool ok[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const int i = base + u * stride;
+      ok[u] = i < npair;
+      q[u] = ok[u] ? __ldg(pair + i) : make_int2(0, 0);
+    }
+    double a[UN][3], b[UN][3];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      if (ok[u]) {
+        a[u][0] = f0[q[u].x]; b[u][0] = f0[q[u].y];
+        a[u][1] = f1[q[u].x]; b[u][1] = f1[q[u].y];
+        a[u][2] = f2[q[u].x]; b[u][2] = f2[q[u].y];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      if (ok[u]) {
+        const double s0 = (0.0 + a[u][0]) + b[u][0], s1 = (0.0 + a[u][1]) + b[u][1],
+                     s2 = (0.0 + a[u][2]) + b[u][2];
+        f0[q[u].x] = s0; f0[q[u].y] = s0;
+        f1[q[u].x] = s1; f1[q[u].y] = s1;
+        f2[q[u].x] = s2; f2[q[u].y] = s2;
+      }
+    }
+  }
+}
+// classes with 3..16 members: W = 4, 8 or 16 ints per class (-1 padded), members summed in list order
+template <int W>
+__global__ void __launch_bounds__(256) gs_wide_kernel(double* __restrict__ f0, double* __restrict__ f1,
+                                                     double* __restrict__ f2, const int4* __restrict__ lst,
+                                                     int ncls) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncls; i += stride) {
+    int d[W];
+#pragma unroll
+    for (int a = 0; a < W / 4; a++) {
+      const int4 q = __ldg(lst + (size_t)i * (W / 4) + a);
+      d[4 * a] = q.x; d[4 * a + 1] = q.y; d[4 * a + 2] = q.z; d[4 * a + 3] = q.w;
+    }
+    double v[W][3];
+#pragma unroll
+    for (int m = 0; m < W; m++)
+      if (d[m] >= 0) { v[m][0] = f0[d[m]]; v[m][1] = f1[d[m]]; v[m][2] = f2[d[m]]; }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < W; m++)
+      if (d[m] >= 0) { s0 += v[m][0]; s1 += v[m][1]; s2 += v[m][2]; }
+#pragma unroll
+    for (int m = 0; m < W; m++)
+      if (d[m] >= 0) { f0[d[m]] = s0; f1[d[m]] = s1; f2[d[m]] = s2; }
   }
 }
 

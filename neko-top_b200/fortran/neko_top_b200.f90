@@ -164,6 +164,30 @@ module neko_top_b200
        type(c_ptr), value :: fx_d, fy_d, fz_d
      end function b200_adv_linear_dealias_compute
 
+     integer(c_int) function b200_adjrhs_set_element_order(handle, nelem, &
+          order) bind(c, name='b200_adjrhs_set_element_order')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       integer(c_int) :: nelem
+       integer(c_int), dimension(*) :: order
+     end function b200_adjrhs_set_element_order
+
+     integer(c_int) function b200_adjrhs_set_gs_fused(handle, flag) &
+          bind(c, name='b200_adjrhs_set_gs_fused')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       integer(c_int) :: flag
+     end function b200_adjrhs_set_gs_fused
+
+     integer(c_int) function b200_adjrhs_gs_info(handle, fused, &
+          classes_in_kernel, classes_total) &
+          bind(c, name='b200_adjrhs_gs_info')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       integer(c_int) :: fused
+       integer(c_int64_t) :: classes_in_kernel, classes_total
+     end function b200_adjrhs_gs_info
+
      integer(c_int) function b200_adjrhs_set_dealias(handle, flag) &
           bind(c, name='b200_adjrhs_set_dealias')
        use, intrinsic :: iso_c_binding

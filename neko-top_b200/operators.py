@@ -379,6 +379,28 @@ class fused_adjoint_rhs_t:
         e = np.ascontiguousarray(elems, dtype=np.int32)
         check(_lib.lib().b200_adjrhs_set_boundary_elements(self._hd.h, _ci(e.size), e.ctypes.data_as(C.POINTER(C.c_int))))
 
+    def set_element_order(self, order):
+        """Processing order of the elements (permutation of 0..nelv-1; None: mesh order)."""
+        if order is None:
+            check(_lib.lib().b200_adjrhs_set_element_order(self._hd.h, _ci(0), None))
+            return
+        o = np.ascontiguousarray(order, dtype=np.int32)
+        check(_lib.lib().b200_adjrhs_set_element_order(self._hd.h, _ci(o.size), o.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def set_gs_fused(self, flag=True):
+        """True: sum the node classes inside the v3 element kernel (experimental); False: separate pass."""
+        self.set_gs_mode(2 if flag else 1)
+
+    def set_gs_mode(self, mode):
+        """2: inside the element kernel, 1: separate pass over the packed class lists (default), 0: CSR kernels."""
+        check(_lib.lib().b200_adjrhs_set_gs_fused(self._hd.h, _ci({2: 1, 1: 0, 0: -1}[int(mode)])))
+
+    def gs_info(self):
+        """(fused, classes summed inside the element kernel, classes in total)."""
+        a, b, c = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().b200_adjrhs_gs_info(self._hd.h, C.byref(a), C.byref(b), C.byref(c)))
+        return bool(a.value), b.value, c.value
+
     def enable_timing(self, flag=True):
         check(_lib.lib().b200_adjrhs_enable_timing(self._hd.h, _ci(flag)))
 

@@ -53,6 +53,21 @@ def config_box(ne, lx=8, deform=0.0):
     return BoxBrick(lx=lx, ne=(ne, ne, ne), deform=deform, name=f"box{ne}^3")
 
 
+def tile_order(brick, tile=(16, 16)):
+    """Processing order for b200_adjrhs_set_element_order: columns of tile[0] x tile[1] elements in (x, y),
+    walked along z, x fastest inside a layer.  The z-neighbour of an element is then tile[0]*tile[1]
+    positions away and the x/y neighbours 1 / tile[0], so a node class completes while the earlier
+    members' right-hand side is still in L2; only faces between columns (1/tile of the x and y faces) meet
+    a neighbour that was stored long ago.  Returns int32 element ids (e = ex + nex*(ey + ney*ez))."""
+    nex, ney, nez = brick.ne
+    tx, ty = min(tile[0], nex), min(tile[1], ney)
+    ex, ey, ez = np.meshgrid(np.arange(nex), np.arange(ney), np.arange(nez), indexing="ij")
+    ex, ey, ez = ex.ravel(), ey.ravel(), ez.ravel()
+    key = ((((ey // ty) * ((nex + tx - 1) // tx) + ex // tx) * nez + ez) * ty + ey % ty) * tx + ex % tx
+    order = np.argsort(key, kind="stable")
+    return (ex[order] + nex * (ey[order] + ney * ez[order])).astype(np.int32)
+
+
 def rank_grid(nranks):
     """configs[3]: GPU grids 1, 2x1x1, 2x2x1, 2x2x2."""
     grids = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}

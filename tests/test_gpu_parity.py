@@ -296,3 +296,75 @@ def test_full_size_properties():
     same = ks[1:] == ks[:-1]
     assert torch.equal(gsrt[1:][same], gsrt[:-1][same])
     op.free()
+
+
+@pytest.mark.parametrize("order_kind", ["mesh", "tile", "random"])
+def test_step_gs_in_kernel(oracle, order_kind):
+    """lx = 8: b200_adjrhs_step sums the node classes inside the element kernel (several windows of
+    element slots, any processing order).  Against the oracle <= 1e-12 and BIT-identical to the separate
+    gather-scatter pass; repeated steps reuse the schedule."""
+    from neko_top_b200 import workloads
+    lx = 8
+    P = Problem(lx, ne=(12, 10, 9), deform=0.02)      # 1080 elements = 3 windows of 444 slots
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
+    ref = [oracle.gs_add(fo[c], cid, nc) for c in range(3)]
+    op, _ = _fused(P)
+    op.gs.init(P.keys.reshape(-1).cuda())
+    if order_kind == "tile":
+        op.set_element_order(workloads.tile_order(P.brick, (4, 4)))
+    elif order_kind == "random":
+        op.set_element_order(np.random.default_rng(3).permutation(P.nelv))
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+    op.set_gs_mode(2)
+    for _ in range(3):
+        op.step(v, ub, f, rho=rho, sens=sens)
+    fused, nin, ntot = op.gs_info()
+    assert fused and nin == ntot > 0
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), ref[c]) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    for mode in (1, 0):        # packed class lists (the default), CSR kernels
+        op.set_gs_mode(mode)
+        g = [_nan(P.n) for _ in range(3)]
+        op.step(v, ub, g, rho=rho)
+        for c in range(3):
+            assert torch.equal(f[c], g[c]), f"gs mode 2 and mode {mode} must be bit-identical"
+    op.free()
+
+
+def test_step_gs_in_kernel_irregular_classes(oracle):
+    """Node classes of every size (3, 5..16 members and > 16, which stay with the list kernel): keys of a
+    box mesh folded modulo a small number so that unrelated nodes are identified."""
+    lx = 8
+    P = Problem(lx, ne=(9, 8, 7), deform=0.02)
+    keys = P.keys.reshape(-1).numpy().copy()
+    rng = np.random.default_rng(17)
+    sel = rng.random(keys.size) < 0.02
+    keys[sel] = keys.max() + 1 + rng.integers(0, 450, sel.sum())       # ~11 members on average, some > 16
+    sel2 = (~sel) & (rng.random(keys.size) < 0.01)
+    keys[sel2] = keys.max() + 1 + rng.integers(0, sel2.sum() // 3 + 1, sel2.sum())   # ~3 members each
+    fo, _, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    cid, nc = oracle.gs_classes(keys)
+    counts = np.bincount(cid)
+    assert counts.max() > 16 and (counts == 3).any() and (counts == 2).any()
+    op, _ = _fused(P)
+    op.gs.init(keys)
+    gcid, gnc = op.gs.classes()
+    assert gnc == nc and np.array_equal(gcid, cid)
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    f = [_nan(P.n) for _ in range(3)]
+    op.set_gs_mode(2)
+    op.step(v, ub, f, rho=rho)
+    fused, nin, ntot = op.gs_info()
+    assert fused and 0 < nin < ntot
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), oracle.gs_add(fo[c], cid, nc)) <= TOL
+    for mode in (1, 0):
+        op.set_gs_mode(mode)
+        g = [_nan(P.n) for _ in range(3)]
+        op.step(v, ub, g, rho=rho)
+        for c in range(3):
+            assert torch.equal(f[c], g[c])
+    op.free()

@@ -50,9 +50,11 @@ def main():
     n = brick.n
     mk = lambda: [torch.full((n,), float("nan"), device=dev, dtype=torch.float64) for _ in range(3)]
     results = {}
-    for mode in ("sequential", "overlap"):
+    for mode in ("sequential", "overlap", "overlap_gs1", "overlap_gs2"):
         if mode == "overlap":
             op.set_boundary_elements(sh.bnd_elem)
+        if mode.startswith("overlap_gs"):      # packed class lists / summation inside the interior kernel
+            op.set_gs_mode(int(mode[-1]))
         f, sens = mk(), torch.empty(n, device=dev, dtype=torch.float64)
         for _ in range(2):
             op.step(d["v"], d["ub"], f, rho=d["rho"], sens=sens)
@@ -63,6 +65,7 @@ def main():
     hub = [a.cpu().pin_memory() for a in d["ub"]]
     hf = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
     hs = torch.empty(n, dtype=torch.float64).pin_memory()
+    op.set_gs_mode(0)
     op.step_host(hv, hub, d["rho"].cpu().pin_memory(), hf, hs)
     results["host"] = [a.numpy() for a in hf] + [hs.numpy()]
 
@@ -88,7 +91,9 @@ def main():
             err = np.linalg.norm(a - b) / np.linalg.norm(b)
             worst = max(worst, err)
         print(f"rank {rank} {mode}: max rel-L2 vs global oracle = {worst:.3e}", flush=True)
-    same = all(np.array_equal(a, b) for a, b in zip(results["sequential"], results["overlap"]))
+    op.set_gs_mode(0)
+    same = all(np.array_equal(a, b) for m in ("overlap", "overlap_gs1", "overlap_gs2")
+               for a, b in zip(results["sequential"], results[m]))
     same_h = all(np.array_equal(a, b) for a, b in zip(results["sequential"], results["host"]))
     t = torch.tensor([worst, 0.0 if (same and same_h) else 1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

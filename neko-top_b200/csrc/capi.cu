@@ -126,6 +126,7 @@ struct Handle {
   int sched_n2 = 0, sched_n4 = 0, sched_n8 = 0, sched_n16 = 0;
   int64_t sched_nfused = 0;        // classes summed inside the element kernel
   unsigned long long* sched_done = nullptr;
+  std::vector<int> sched_elem_last;   // host copy: per position, the last position whose classes touch it (kind 1)
 
   // host-staged step
   double* stage[11] = {};
@@ -664,6 +665,21 @@ int build_gs_schedule(Handle* h, const int* list, int nlist) {
     CK(cudaGetLastError());
   }
   if (int r = dmalloc(&h->sched_done, (size_t)nlist + 1)) return r;
+  h->sched_elem_last.clear();
+  if (!list && nlist == h->nelv) {          // mesh order: what the pipelined host step needs
+    int* d_last = nullptr;
+    if (int r = dmalloc(&d_last, (size_t)h->nelv)) return r;
+    gs_iota_kernel<<<grid_for(h->nelv, threads, h->num_sm, 8), threads, 0, st>>>(d_last, h->nelv);
+    LAUNCHED();
+    gs_elem_last_kernel<<<grid_for(nc, threads, h->num_sm, 8), threads, 0, st>>>(
+        h->gs_off, h->gs_dof, h->gs_skip, nc, d_pos, h->lx * h->lx * h->lx, h->nelv - 1, d_last);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    h->sched_elem_last.resize(h->nelv);
+    CK(cudaMemcpyAsync(h->sched_elem_last.data(), d_last, sizeof(int) * (size_t)h->nelv, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_last));
+  }
   CK(cudaStreamSynchronize(st));
   CK(cudaFree(d_pos)); CK(cudaFree(d_cls)); CK(cudaFree(d_cls2)); CK(cudaFree(d_key)); CK(cudaFree(d_key2));
   CK(cudaFree(d_bstart));
@@ -675,33 +691,42 @@ int build_gs_schedule(Handle* h, const int* list, int nlist) {
   return B200_OK;
 }
 
-// separate gather-scatter pass over the packed lists of the schedule (3 fields)
-int gs_packed(Handle* h, double* f0, double* f1, double* f2) {
+// separate gather-scatter pass over the packed lists of the schedule (3 fields); entries [lo[b], hi[b]) of
+// list b = 0..3 (pairs, quads, octs, hexes)
+int gs_packed_range(Handle* h, double* f0, double* f1, double* f2, const int lo[4], const int hi[4]) {
   const int threads = 256;
-  if (h->sched_n2 > 0) {
+  if (hi[0] > lo[0]) {
     constexpr int UN = 4;
-    const int grid = grid_for((h->sched_n2 + UN - 1) / UN, threads, h->num_sm, 8);
-    gs_pairs_kernel<UN><<<grid, threads, 0, h->stream>>>(f0, f1, f2, reinterpret_cast<const int2*>(h->sched_pair),
-                                                         h->sched_n2);
+    const int cnt = hi[0] - lo[0];
+    const int grid = grid_for((cnt + UN - 1) / UN, threads, h->num_sm, 8);
+    gs_pairs_kernel<UN><<<grid, threads, 0, h->stream>>>(
+        f0, f1, f2, reinterpret_cast<const int2*>(h->sched_pair) + lo[0], cnt);
     LAUNCHED();
   }
-  if (h->sched_n4 > 0) {
-    gs_wide_kernel<4><<<grid_for(h->sched_n4, threads, h->num_sm, 8), threads, 0, h->stream>>>(
-        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_quad), h->sched_n4);
+  if (hi[1] > lo[1]) {
+    const int cnt = hi[1] - lo[1];
+    gs_wide_kernel<4><<<grid_for(cnt, threads, h->num_sm, 8), threads, 0, h->stream>>>(
+        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_quad) + lo[1], cnt);
     LAUNCHED();
   }
-  if (h->sched_n8 > 0) {
-    gs_wide_kernel<8><<<grid_for(h->sched_n8, threads, h->num_sm, 8), threads, 0, h->stream>>>(
-        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_oct), h->sched_n8);
+  if (hi[2] > lo[2]) {
+    const int cnt = hi[2] - lo[2];
+    gs_wide_kernel<8><<<grid_for(cnt, threads, h->num_sm, 8), threads, 0, h->stream>>>(
+        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_oct) + 2 * (size_t)lo[2], cnt);
     LAUNCHED();
   }
-  if (h->sched_n16 > 0) {
-    gs_wide_kernel<16><<<grid_for(h->sched_n16, threads, h->num_sm, 4), threads, 0, h->stream>>>(
-        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_hex), h->sched_n16);
+  if (hi[3] > lo[3]) {
+    const int cnt = hi[3] - lo[3];
+    gs_wide_kernel<16><<<grid_for(cnt, threads, h->num_sm, 4), threads, 0, h->stream>>>(
+        f0, f1, f2, reinterpret_cast<const int4*>(h->sched_hex) + 4 * (size_t)lo[3], cnt);
     LAUNCHED();
   }
   CK(cudaGetLastError());
   return B200_OK;
+}
+int gs_packed(Handle* h, double* f0, double* f1, double* f2) {
+  const int lo[4] = {0, 0, 0, 0}, hi[4] = {h->sched_n2, h->sched_n4, h->sched_n8, h->sched_n16};
+  return gs_packed_range(h, f0, f1, f2, lo, hi);
 }
 
 // classes with more than 16 members are not in the in-kernel schedule
@@ -975,8 +1000,8 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
       if (int r = gs_leftover(h, f0, f1, f2)) return r;
     } else if (h->nclass > 0) {
       const int threads = 256, grid = grid_for(h->nclass, threads, h->num_sm, 8);
-      gs_op_skip_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->gs_skip,
-                                                             h->nclass);
+      gs_op_kernel<3, 1><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass,
+                                                           h->gs_skip);
       LAUNCHED();
       CK(cudaGetLastError());
     }
@@ -1564,19 +1589,51 @@ int b200_adjrhs_step_host(void* handle, const double* vx, const double* vy, cons
   const double* in[7] = {vx, vy, vz, vxb, vyb, vzb, rho};
   double** st = h->stage;   // 0..6 inputs, 7..9 f, 10 sens
   // element chunks: copy chunk c+1 while chunk c computes; sens goes back as soon as its chunk is done
-  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(16, h->nelv / 1024));
+  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(16, h->nelv / 256));
   while ((int)h->ev_h2d.size() < nchunk) {
     cudaEvent_t a, b;
     CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     h->ev_h2d.push_back(a); h->ev_k.push_back(b);
   }
+  // Single GPU, mesh order, no point-zone mask: the direct-stiffness summation is pipelined too.  After chunk
+  // c the classes that COMPLETE in it are summed (they are contiguous ranges of the schedule's packed lists,
+  // which are sorted by completing position), and f goes back for every leading element whose classes are
+  // all summed -- so the device->host copy of f overlaps the host->device copy of the later chunks instead
+  // of waiting for the whole mesh.  Same sums in the same order: bit-identical to the one-pass path.
+  const bool masked = h->if_lube && h->lube_mask_size > 0;
+  bool pipe_gs = !h->comm && h->order.empty() && !masked && h->nclass > 0 && nchunk > 1;
+  if (pipe_gs) {
+    if (!h->sched_valid || h->sched_kind != 1) {
+      if (int r = build_gs_schedule(h, nullptr, h->nelv)) return r;
+      h->sched_kind = 1;
+    }
+    pipe_gs = h->sched_valid && (int)h->sched_elem_last.size() == h->nelv;
+  }
+  std::vector<int> cb(nchunk + 1), ready(nchunk + 1, 0);
+  for (int c = 0; c <= nchunk; c++) cb[c] = (int)((int64_t)h->nelv * c / nchunk);
+  std::vector<int> eo(4 * (size_t)(nchunk + 1), 0);
+  if (pipe_gs) {
+    for (int c = 0; c <= nchunk; c++)
+      CK(cudaMemcpyAsync(&eo[4 * c], h->sched_eoff + 4 * (size_t)cb[c], 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                         h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int m = 0, run_max = -1;                  // ready[c+1]: elements [0, m) are final after chunk c
+    for (int c = 0; c < nchunk; c++) {
+      while (m < h->nelv && std::max(run_max, h->sched_elem_last[m]) < cb[c + 1]) {
+        run_max = std::max(run_max, h->sched_elem_last[m]);
+        m++;
+      }
+      ready[c + 1] = m;
+    }
+  }
   // the caller's stream must be idle with respect to the staging buffers
   CK(cudaEventRecord(h->ev_done, h->stream));
   CK(cudaStreamWaitEvent(h->h2d_stream, h->ev_done, 0));
   CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done, 0));
+  double* out[3] = {fx, fy, fz};
   for (int c = 0; c < nchunk; c++) {
-    const int e0 = (int)((int64_t)h->nelv * c / nchunk), e1 = (int)((int64_t)h->nelv * (c + 1) / nchunk);
+    const int e0 = cb[c], e1 = cb[c + 1];
     const size_t o = (size_t)e0 * N, cnt = (size_t)(e1 - e0) * N;
     for (int i = 0; i < 7; i++)
       CK(cudaMemcpyAsync(st[i] + o, in[i] + o, cnt * 8, cudaMemcpyHostToDevice, h->h2d_stream));
@@ -1586,23 +1643,33 @@ int b200_adjrhs_step_host(void* handle, const double* vx, const double* vy, cons
                              nullptr, st[7], st[8], st[9], sens ? st[10] : nullptr, nullptr, e1 - e0);
     a.elem_begin = e0;
     if (int r = launch_fused(h, a)) return r;
-    if (sens) {
+    if (pipe_gs) {
+      if (int r = gs_packed_range(h, st[7], st[8], st[9], &eo[4 * c], &eo[4 * (c + 1)])) return r;
+      if (c == nchunk - 1) if (int r = gs_leftover(h, st[7], st[8], st[9])) return r;
+    }
+    if (sens || pipe_gs) {
       CK(cudaEventRecord(h->ev_k[c], h->stream));
       CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_k[c], 0));
-      CK(cudaMemcpyAsync(sens + o, st[10] + o, cnt * 8, cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
+    if (sens) CK(cudaMemcpyAsync(sens + o, st[10] + o, cnt * 8, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (pipe_gs && ready[c + 1] > ready[c]) {
+      const size_t fo = (size_t)ready[c] * N, fc = (size_t)(ready[c + 1] - ready[c]) * N;
+      for (int i = 0; i < 3; i++)
+        CK(cudaMemcpyAsync(out[i] + fo, st[7 + i] + fo, fc * 8, cudaMemcpyDeviceToHost, h->d2h_stream));
     }
   }
-  {
-    LaunchArgs a = make_args(st[0], st[1], st[2], st[3], st[4], st[5], st[6], nullptr, nullptr, nullptr,
-                             nullptr, st[7], st[8], st[9], nullptr, nullptr, h->nelv);
-    if (int r = masked_lube_post(h, a)) return r;
+  if (!pipe_gs) {
+    {
+      LaunchArgs a = make_args(st[0], st[1], st[2], st[3], st[4], st[5], st[6], nullptr, nullptr, nullptr,
+                               nullptr, st[7], st[8], st[9], nullptr, nullptr, h->nelv);
+      if (int r = masked_lube_post(h, a)) return r;
+    }
+    if (int r = gs_launch(h, st[7], st[8], st[9], 3)) return r;
+    if (int r = gs_exchange(h, st[7], st[8], st[9], 3)) return r;
+    if (int r = gs_finish_exchange(h, st[7], st[8], st[9], 3)) return r;
+    for (int i = 0; i < 3; i++)
+      CK(cudaMemcpyAsync(out[i], st[7 + i], n * 8, cudaMemcpyDeviceToHost, h->stream));
   }
-  if (int r = gs_launch(h, st[7], st[8], st[9], 3)) return r;
-  if (int r = gs_exchange(h, st[7], st[8], st[9], 3)) return r;
-  if (int r = gs_finish_exchange(h, st[7], st[8], st[9], 3)) return r;
-  double* out[3] = {fx, fy, fz};
-  for (int i = 0; i < 3; i++)
-    CK(cudaMemcpyAsync(out[i], st[7 + i], n * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->d2h_stream));
   CK(cudaStreamSynchronize(h->stream));
   return B200_OK;

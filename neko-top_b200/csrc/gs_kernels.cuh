@@ -70,7 +70,8 @@ __global__ void gs_classid_kernel(const int* __restrict__ rep, const int* __rest
 // latency of the chain offsets -> members -> values, not by bandwidth.
 template <int NF, int UN = 2>
 __global__ void gs_op_kernel(double* f0, double* f1, double* f2,
-                             const int* __restrict__ off, const int* __restrict__ dof, int nclass) {
+                             const int* __restrict__ off, const int* __restrict__ dof, int nclass,
+                             const unsigned char* __restrict__ skip = nullptr) {
   const int stride = gridDim.x * blockDim.x;
   for (int c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < nclass; c0 += stride * UN) {
     int b[UN], e[UN], d0[UN], d1[UN];
@@ -78,7 +79,7 @@ __global__ void gs_op_kernel(double* f0, double* f1, double* f2,
     for (int u = 0; u < UN; u++) {
       const int c = c0 + u * stride;
       b[u] = e[u] = 0;
-      if (c < nclass) { b[u] = off[c]; e[u] = off[c + 1]; }
+      if (c < nclass && !(skip && skip[c])) { b[u] = off[c]; e[u] = off[c + 1]; }
     }
 #pragma unroll
     for (int u = 0; u < UN; u++) {
@@ -214,29 +215,6 @@ __global__ void gs_op_list_kernel(double* f0, double* f1, double* f2,
     }
   }
 }
-// gs over all classes except the flagged ones
-template <int NF>
-__global__ void gs_op_skip_kernel(double* f0, double* f1, double* f2,
-                                  const int* __restrict__ off, const int* __restrict__ dof,
-                                  const unsigned char* __restrict__ skip, int nclass) {
-  const int stride = gridDim.x * blockDim.x;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
-    if (skip[c]) continue;
-    const int b = off[c], e = off[c + 1];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int m = b; m < e; m++) {
-      const int d = dof[m];
-      s0 += f0[d];
-      if (NF > 1) { s1 += f1[d]; s2 += f2[d]; }
-    }
-    for (int m = b; m < e; m++) {
-      const int d = dof[m];
-      f0[d] = s0;
-      if (NF > 1) { f1[d] = s1; f2[d] = s2; }
-    }
-  }
-}
-
 // ---- schedule of the in-kernel direct-stiffness summation (adjrhs_kernel_v3.cuh, FLAG_GS) ------------------
 // pos[e] = position of element e in the processing list (-1: not in the list == stored before the launch)
 __global__ void gs_pos_kernel(const int* __restrict__ order, int norder, int* __restrict__ pos) {
@@ -304,6 +282,23 @@ __global__ void gs_fill_kernel(const int* __restrict__ cls, const int* __restric
     else if (i < bstart[3]) { dst = oct + 8 * (size_t)(i - bstart[2]); width = 8; }
     else { dst = hex + 16 * (size_t)(i - bstart[3]); width = 16; }
     for (int m = 0; m < width; m++) dst[m] = m < deg ? dof[b + m] : -1;
+  }
+}
+
+// last[e] = largest completing position among the classes that touch element e (classes with more than 16
+// members count as completing at `late`): f of element e is final once the classes of all positions
+// <= last[e] are summed.  last[] must be initialised with the element's own position.
+__global__ void gs_elem_last_kernel(const int* __restrict__ off, const int* __restrict__ dof,
+                                    const unsigned char* __restrict__ skip, int nclass,
+                                    const int* __restrict__ pos, int npts, int late, int* __restrict__ last) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
+    if (skip && skip[c]) continue;
+    const int b = off[c], e = off[c + 1];
+    int pm = 0;
+    for (int m = b; m < e; m++) pm = max(pm, pos[dof[m] / npts]);
+    if (e - b > 16) pm = late;
+    for (int m = b; m < e; m++) atomicMax(last + dof[m] / npts, pm);
   }
 }
 

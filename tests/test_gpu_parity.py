@@ -298,6 +298,22 @@ def test_full_size_properties():
     op.free()
 
 
+def _check_step_host(op, v, ub, rho, f, sens):
+    """b200_adjrhs_step_host (host buffers; several element chunks, summation and copies pipelined when the
+    elements are in mesh order) must reproduce the device-resident step bit for bit."""
+    n = f[0].numel()
+    hv = [a.cpu().pin_memory() for a in v]
+    hub = [a.cpu().pin_memory() for a in ub]
+    hf = [torch.full((n,), float("nan"), dtype=torch.float64).pin_memory() for _ in range(3)]
+    hs = torch.full((n,), float("nan"), dtype=torch.float64).pin_memory() if sens is not None else None
+    for _ in range(2):
+        op.step_host(hv, hub, rho.cpu().pin_memory(), hf, hs)
+    for c in range(3):
+        assert torch.equal(hf[c], f[c].cpu()), "host-buffer step differs from the device step"
+    if sens is not None:
+        assert torch.equal(hs, sens.cpu())
+
+
 @pytest.mark.parametrize("order_kind", ["mesh", "tile", "random"])
 def test_step_gs_in_kernel(oracle, order_kind):
     """lx = 8: b200_adjrhs_step sums the node classes inside the element kernel (several windows of
@@ -331,6 +347,7 @@ def test_step_gs_in_kernel(oracle, order_kind):
         op.step(v, ub, g, rho=rho)
         for c in range(3):
             assert torch.equal(f[c], g[c]), f"gs mode 2 and mode {mode} must be bit-identical"
+    _check_step_host(op, v, ub, rho, f, sens)
     op.free()
 
 
@@ -367,4 +384,5 @@ def test_step_gs_in_kernel_irregular_classes(oracle):
         op.step(v, ub, g, rho=rho)
         for c in range(3):
             assert torch.equal(f[c], g[c])
+    _check_step_host(op, v, ub, rho, f, None)
     op.free()

@@ -317,7 +317,8 @@ def run_b200(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "adjrhs_fused_kernel (element kernel; 168 B/DOF algorithmic)",
+                "kernel": ("adjrhs_v3_kernel<3,4,2,14,168> (fused element kernel, DMMA contractions; "
+                           "168 B/DOF algorithmic)") if lx == 8 else "adjrhs_v2_kernel (fused element kernel; 168 B/DOF algorithmic)",
                 "kernel_ms": elem_ms, "gs_ms": gs_ms, "algorithmic_bytes_per_launch": n * bpd,
                 "peak_source": peak_src,
                 "step_GBps": n * sem.algorithmic_bytes_per_dof(lx, True) / (ms_step * 1e-3) / 1e9}

@@ -162,6 +162,35 @@ int b200_sensitivity(void* sens, const void* u, const void* v, const void* w, co
  * (field_copy), in one pass.  Synchronises the stream (it returns a host scalar). */
 int b200_steady_field_update(double* result, const void* x, void* x_old, const int* n, void* stream);
 
+/* ---- explicit time scheme around the RHS (adjoint/adjoint_pnpn.f90:665-666,688-696) --
+ * Neko's rhs_maker types, argument order of the reference's call sites; all fields are device pointers of
+ * *n doubles; coefficient arrays are HOST pointers.
+ * sumab%compute_fluid(u_e,v_e,w_e, u,v,w, ulag,vlag,wlag, ext_bdf%advection_coeffs, nadv):
+ *   u_e = ab(1)*u + ab(2)*ulag(1) [+ ab(3)*ulag(2) if *nab == 3]; ulag1 = ulag%lf(1)%x_d, ulag2 = ulag%lf(2)%x_d */
+int b200_sumab(void* ue, void* ve, void* we, const void* u, const void* v, const void* w,
+               const void* ulag1, const void* vlag1, const void* wlag1,
+               const void* ulag2, const void* vlag2, const void* wlag2,
+               const double* ab, const int* nab, const int* n, void* stream);
+/* makeabf%compute_fluid(abx1,aby1,abz1, abx2,aby2,abz2, f_x,f_y,f_z, rho, advection_coeffs, n):
+ *   ta = ext(2)*ab1 + ext(3)*ab2; ab2 = ab1; ab1 = f; f = (ext(1)*f + ta)*rho */
+int b200_makeabf(void* abx1, void* aby1, void* abz1, void* abx2, void* aby2, void* abz2,
+                 void* fx, void* fy, void* fz, const double* rho, const double* ext, const int* n,
+                 void* stream);
+/* makebdf%compute_fluid(ulag,vlag,wlag, f_x,f_y,f_z, u,v,w, B, rho, dt, diffusion_coeffs, ndiff, n):
+ *   tb = u*B*bd(2) + sum_{ilag=2..nbd} ulag(ilag-1)*B*bd(ilag+1); f = f + tb*(rho/dt); bd has *nbd+1 entries */
+int b200_makebdf(const void* ulag1, const void* vlag1, const void* wlag1,
+                 const void* ulag2, const void* vlag2, const void* wlag2,
+                 void* fx, void* fy, void* fz, const void* u, const void* v, const void* w,
+                 const void* B, const double* rho, const double* dt, const double* bd, const int* nbd,
+                 const int* n, void* stream);
+/* both in ONE pass over f (the two calls above back to back, adjoint_pnpn.f90:688-696) */
+int b200_makeabf_bdf(void* abx1, void* aby1, void* abz1, void* abx2, void* aby2, void* abz2,
+                     const void* ulag1, const void* vlag1, const void* wlag1,
+                     const void* ulag2, const void* vlag2, const void* wlag2,
+                     void* fx, void* fy, void* fz, const void* u, const void* v, const void* w,
+                     const void* B, const double* rho, const double* dt, const double* ext,
+                     const double* bd, const int* nbd, const int* n, void* stream);
+
 /* ---- gather-scatter: gs_t%op(., GS_OP_ADD) (adjoint/adjoint_pnpn.f90:725,755-757) ------------
  * key: global node id of every local dof (n = nelv*lx^3 int64), device pointer if *on_device.
  * Two dofs are summed iff their keys are equal (SURVEY.md 8c "node equivalence classes"). */

@@ -20,6 +20,7 @@ SYMBOLS = [
     "b200_brinkman_compute",
     "b200_lube_compute", "b200_opcolv", "b200_ramp_forward", "b200_ramp_backward",
     "b200_sensitivity", "b200_steady_field_update",
+    "b200_sumab", "b200_makeabf", "b200_makebdf", "b200_makeabf_bdf",
     "b200_gs_init", "b200_gs_get_classes", "b200_gs_op", "b200_gs_op3",
     "b200_comm_unique_id", "b200_comm_init", "b200_gs_init_shared",
     "b200_adjrhs_set_boundary_elements", "b200_adjrhs_set_element_order", "b200_adjrhs_gs_info", "b200_adjrhs_set_gs_fused", "b200_adjrhs_enable_timing", "b200_adjrhs_get_timing",

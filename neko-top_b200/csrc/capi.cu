@@ -1275,6 +1275,83 @@ int b200_steady_field_update(double* result, const void* x, void* x_old, const i
   return B200_OK;
 }
 
+// ---- explicit time scheme around the RHS ---------------------------------------------------------------
+static int abf_bdf_launch(void* fx, void* fy, void* fz, void* abx1, void* aby1, void* abz1, void* abx2,
+                          void* aby2, void* abz2, int do_abf, const double* ext, int do_bdf, const void* u,
+                          const void* v, const void* w, const void* ul1, const void* vl1, const void* wl1,
+                          const void* ul2, const void* vl2, const void* wl2, const void* B, double rho,
+                          double dt, const double* bd, int nbd, int n, void* stream) {
+  Vec3Ptr f{{(double*)fx, (double*)fy, (double*)fz}};
+  Vec3Ptr a1{{(double*)abx1, (double*)aby1, (double*)abz1}}, a2{{(double*)abx2, (double*)aby2, (double*)abz2}};
+  Vec3CPtr uu{{(const double*)u, (const double*)v, (const double*)w}};
+  Vec3CPtr l1{{(const double*)ul1, (const double*)vl1, (const double*)wl1}};
+  Vec3CPtr l2{{(const double*)ul2, (const double*)vl2, (const double*)wl2}};
+  const int threads = 256;
+  abf_bdf_kernel<<<grid_for(n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+      f, a1, a2, do_abf, do_abf ? ext[0] : 0.0, do_abf ? ext[1] : 0.0, do_abf ? ext[2] : 0.0, do_bdf, uu, l1, l2,
+      (const double*)B, rho, do_bdf ? rho / dt : 0.0, do_bdf ? bd[1] : 0.0, (do_bdf && nbd >= 2) ? bd[2] : 0.0,
+      (do_bdf && nbd >= 3) ? bd[3] : 0.0, nbd, (int64_t)n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_sumab(void* ue, void* ve, void* we, const void* u, const void* v, const void* w, const void* ulag1,
+               const void* vlag1, const void* wlag1, const void* ulag2, const void* vlag2, const void* wlag2,
+               const double* ab, const int* nab, const int* n, void* stream) {
+  if (!ue || !ve || !we || !u || !v || !w || !ulag1 || !vlag1 || !wlag1 || !ab || !nab || !n)
+    return fail(B200_ERR_ARG, "sumab: null argument");
+  if (*nab < 2 || *nab > 3) return fail(B200_ERR_ARG, "sumab: nab=%d (2 or 3)", *nab);
+  if (*nab == 3 && (!ulag2 || !vlag2 || !wlag2)) return fail(B200_ERR_ARG, "sumab: nab=3 needs the second lag");
+  Vec3Ptr e{{(double*)ue, (double*)ve, (double*)we}};
+  Vec3CPtr uu{{(const double*)u, (const double*)v, (const double*)w}};
+  Vec3CPtr l1{{(const double*)ulag1, (const double*)vlag1, (const double*)wlag1}};
+  Vec3CPtr l2{{(const double*)ulag2, (const double*)vlag2, (const double*)wlag2}};
+  const int threads = 256;
+  sumab_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, (cudaStream_t)stream>>>(
+      e, uu, l1, l2, ab[0], ab[1], *nab == 3 ? ab[2] : 0.0, *nab, (int64_t)*n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_makeabf(void* abx1, void* aby1, void* abz1, void* abx2, void* aby2, void* abz2, void* fx, void* fy,
+                 void* fz, const double* rho, const double* ext, const int* n, void* stream) {
+  if (!abx1 || !aby1 || !abz1 || !abx2 || !aby2 || !abz2 || !fx || !fy || !fz || !rho || !ext || !n)
+    return fail(B200_ERR_ARG, "makeabf: null argument");
+  return abf_bdf_launch(fx, fy, fz, abx1, aby1, abz1, abx2, aby2, abz2, 1, ext, 0, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, *rho, 1.0, nullptr, 0, *n,
+                        stream);
+}
+
+int b200_makebdf(const void* ulag1, const void* vlag1, const void* wlag1, const void* ulag2, const void* vlag2,
+                 const void* wlag2, void* fx, void* fy, void* fz, const void* u, const void* v, const void* w,
+                 const void* B, const double* rho, const double* dt, const double* bd, const int* nbd,
+                 const int* n, void* stream) {
+  if (!fx || !fy || !fz || !u || !v || !w || !B || !rho || !dt || !bd || !nbd || !n)
+    return fail(B200_ERR_ARG, "makebdf: null argument");
+  if (*nbd < 1 || *nbd > 3) return fail(B200_ERR_ARG, "makebdf: nbd=%d (1..3)", *nbd);
+  if ((*nbd >= 2 && (!ulag1 || !vlag1 || !wlag1)) || (*nbd >= 3 && (!ulag2 || !vlag2 || !wlag2)))
+    return fail(B200_ERR_ARG, "makebdf: lag fields missing for nbd=%d", *nbd);
+  return abf_bdf_launch(fx, fy, fz, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 1, u, v, w,
+                        ulag1, vlag1, wlag1, ulag2, vlag2, wlag2, B, *rho, *dt, bd, *nbd, *n, stream);
+}
+
+int b200_makeabf_bdf(void* abx1, void* aby1, void* abz1, void* abx2, void* aby2, void* abz2, const void* ulag1,
+                     const void* vlag1, const void* wlag1, const void* ulag2, const void* vlag2,
+                     const void* wlag2, void* fx, void* fy, void* fz, const void* u, const void* v,
+                     const void* w, const void* B, const double* rho, const double* dt, const double* ext,
+                     const double* bd, const int* nbd, const int* n, void* stream) {
+  if (!abx1 || !aby1 || !abz1 || !abx2 || !aby2 || !abz2 || !fx || !fy || !fz || !u || !v || !w || !B || !rho ||
+      !dt || !ext || !bd || !nbd || !n)
+    return fail(B200_ERR_ARG, "makeabf_bdf: null argument");
+  if (*nbd < 1 || *nbd > 3) return fail(B200_ERR_ARG, "makeabf_bdf: nbd=%d (1..3)", *nbd);
+  if ((*nbd >= 2 && (!ulag1 || !vlag1 || !wlag1)) || (*nbd >= 3 && (!ulag2 || !vlag2 || !wlag2)))
+    return fail(B200_ERR_ARG, "makeabf_bdf: lag fields missing for nbd=%d", *nbd);
+  return abf_bdf_launch(fx, fy, fz, abx1, aby1, abz1, abx2, aby2, abz2, 1, ext, 1, u, v, w, ulag1, vlag1, wlag1,
+                        ulag2, vlag2, wlag2, B, *rho, *dt, bd, *nbd, *n, stream);
+}
+
 // ---- gather-scatter set-up ---------------------------------------------------------------------
 int b200_gs_init(void* handle, const int64_t* key, const int* on_device) {
   if (!handle || !key) return fail(B200_ERR_ARG, "gs_init: null argument");

@@ -169,4 +169,52 @@ __global__ void steady_update_kernel(double* __restrict__ result, const double* 
   }
 }
 
+// ---- explicit time scheme around the RHS (adjoint_pnpn.f90:665-666,688-696; Neko rhs_maker types) --------
+struct Vec3Ptr { double* p[3]; };
+struct Vec3CPtr { const double* p[3]; };
+
+// sumab%compute_fluid: u_e = ab1*u + ab2*ulag1 [+ ab3*ulag2]
+__global__ void sumab_kernel(Vec3Ptr ue, Vec3CPtr u, Vec3CPtr l1, Vec3CPtr l2, double ab1, double ab2, double ab3,
+                             int nab, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double r = ab1 * u.p[c][i] + ab2 * l1.p[c][i];
+      if (nab == 3) r = r + ab3 * l2.p[c][i];
+      ue.p[c][i] = r;
+    }
+  }
+}
+// makeabf%compute_fluid [+ makebdf%compute_fluid when do_bdf]: one pass over f instead of two
+//   ta = ext2*f_lag + ext3*f_laglag ; f_laglag = f_lag ; f_lag = f ; f = (ext1*f + ta)*rho
+//   tb = u*B*bd2 [+ ulag1*B*bd3] [+ ulag2*B*bd4] ; f = f + tb*(rho/dt)
+__global__ void abf_bdf_kernel(Vec3Ptr f, Vec3Ptr ab1, Vec3Ptr ab2, int do_abf, double ext1, double ext2,
+                               double ext3, int do_bdf, Vec3CPtr u, Vec3CPtr l1, Vec3CPtr l2,
+                               const double* __restrict__ B, double rho, double rho_dt, double bd2, double bd3,
+                               double bd4, int nbd, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double b = do_bdf ? B[i] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double fv = f.p[c][i];
+      if (do_abf) {
+        const double a1 = ab1.p[c][i], a2 = ab2.p[c][i];
+        const double ta = ext2 * a1 + ext3 * a2;
+        ab2.p[c][i] = a1;
+        ab1.p[c][i] = fv;
+        fv = (ext1 * fv + ta) * rho;
+      }
+      if (do_bdf) {
+        double tb = u.p[c][i] * b * bd2;
+        if (nbd >= 2) tb = tb + l1.p[c][i] * b * bd3;
+        if (nbd >= 3) tb = tb + l2.p[c][i] * b * bd4;
+        fv = fv + tb * rho_dt;
+      }
+      f.p[c][i] = fv;
+    }
+  }
+}
+
 }  // namespace b200

@@ -164,6 +164,55 @@ module neko_top_b200
        type(c_ptr), value :: fx_d, fy_d, fz_d
      end function b200_adv_linear_dealias_compute
 
+     integer(c_int) function b200_sumab(ue_d, ve_d, we_d, u_d, v_d, w_d, &
+          ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d, ab, nab, n, &
+          stream) bind(c, name='b200_sumab')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: ue_d, ve_d, we_d, u_d, v_d, w_d
+       type(c_ptr), value :: ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d
+       real(c_double), dimension(*) :: ab
+       integer(c_int) :: nab, n
+       type(c_ptr), value :: stream
+     end function b200_sumab
+
+     integer(c_int) function b200_makeabf(abx1_d, aby1_d, abz1_d, abx2_d, &
+          aby2_d, abz2_d, fx_d, fy_d, fz_d, rho, ext, n, stream) &
+          bind(c, name='b200_makeabf')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: abx1_d, aby1_d, abz1_d, abx2_d, aby2_d, abz2_d
+       type(c_ptr), value :: fx_d, fy_d, fz_d
+       real(c_double) :: rho
+       real(c_double), dimension(*) :: ext
+       integer(c_int) :: n
+       type(c_ptr), value :: stream
+     end function b200_makeabf
+
+     integer(c_int) function b200_makebdf(ulag1_d, vlag1_d, wlag1_d, ulag2_d, &
+          vlag2_d, wlag2_d, fx_d, fy_d, fz_d, u_d, v_d, w_d, B_d, rho, dt, bd, &
+          nbd, n, stream) bind(c, name='b200_makebdf')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d
+       type(c_ptr), value :: fx_d, fy_d, fz_d, u_d, v_d, w_d, B_d
+       real(c_double) :: rho, dt
+       real(c_double), dimension(*) :: bd
+       integer(c_int) :: nbd, n
+       type(c_ptr), value :: stream
+     end function b200_makebdf
+
+     integer(c_int) function b200_makeabf_bdf(abx1_d, aby1_d, abz1_d, abx2_d, &
+          aby2_d, abz2_d, ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d, &
+          fx_d, fy_d, fz_d, u_d, v_d, w_d, B_d, rho, dt, ext, bd, nbd, n, &
+          stream) bind(c, name='b200_makeabf_bdf')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: abx1_d, aby1_d, abz1_d, abx2_d, aby2_d, abz2_d
+       type(c_ptr), value :: ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d
+       type(c_ptr), value :: fx_d, fy_d, fz_d, u_d, v_d, w_d, B_d
+       real(c_double) :: rho, dt
+       real(c_double), dimension(*) :: ext, bd
+       integer(c_int) :: nbd, n
+       type(c_ptr), value :: stream
+     end function b200_makeabf_bdf
+
      integer(c_int) function b200_adjrhs_set_element_order(handle, nelem, &
           order) bind(c, name='b200_adjrhs_set_element_order')
        use, intrinsic :: iso_c_binding

@@ -255,6 +255,57 @@ def compute_sensitivity(sens, u, v, w, u_adj, v_adj, w_adj, K_obj=1.0, if_lube=T
                                       _ptr(w_adj), _cd(K_obj), _ci(if_lube), _ci(sens.numel()), _stream_ptr()))
 
 
+# ---- explicit time scheme around the RHS (Neko rhs_maker types; adjoint_pnpn.f90:665-666,688-696) ---------
+def _dv(a):
+    v = np.ascontiguousarray(a, dtype=np.float64)
+    return v, v.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _p3(a):
+    return [None] * 3 if a is None else [_ptr(t) for t in a]
+
+
+class rhs_maker_sumab_t:
+    """sumab%compute_fluid(u_e, v_e, w_e, u, v, w, ulag, vlag, wlag, ab, nab); *lag = (lag1[, lag2]) tensors."""
+
+    def compute_fluid(self, u_e, v_e, w_e, u, v, w, ulag, vlag, wlag, ab, nab):
+        _, abp = _dv(list(ab) + [0.0] * (3 - len(ab)))
+        l1 = [ulag[0], vlag[0], wlag[0]]
+        l2 = [ulag[1], vlag[1], wlag[1]] if nab == 3 else None
+        check(_lib.lib().b200_sumab(_ptr(u_e), _ptr(v_e), _ptr(w_e), _ptr(u), _ptr(v), _ptr(w), *_p3(l1), *_p3(l2),
+                                    abp, _ci(nab), _ci(u.numel()), _stream_ptr()))
+
+
+class rhs_maker_ext_t:
+    """makeabf%compute_fluid(abx1, aby1, abz1, abx2, aby2, abz2, f_x, f_y, f_z, rho, ext, n)."""
+
+    def compute_fluid(self, abx1, aby1, abz1, abx2, aby2, abz2, fx, fy, fz, rho, ext, n=None):
+        _, ep = _dv(ext)
+        check(_lib.lib().b200_makeabf(_ptr(abx1), _ptr(aby1), _ptr(abz1), _ptr(abx2), _ptr(aby2), _ptr(abz2),
+                                      _ptr(fx), _ptr(fy), _ptr(fz), _cd(rho), ep, _ci(fx.numel()), _stream_ptr()))
+
+
+class rhs_maker_bdf_t:
+    """makebdf%compute_fluid(ulag, vlag, wlag, f_x, f_y, f_z, u, v, w, B, rho, dt, bd, nbd, n)."""
+
+    def compute_fluid(self, ulag, vlag, wlag, fx, fy, fz, u, v, w, B, rho, dt, bd, nbd, n=None):
+        _, bp = _dv(list(bd) + [0.0] * (4 - len(bd)))
+        l1 = [ulag[0], vlag[0], wlag[0]] if nbd >= 2 else None
+        l2 = [ulag[1], vlag[1], wlag[1]] if nbd >= 3 else None
+        check(_lib.lib().b200_makebdf(*_p3(l1), *_p3(l2), _ptr(fx), _ptr(fy), _ptr(fz), _ptr(u), _ptr(v), _ptr(w),
+                                      _ptr(B), _cd(rho), _cd(dt), bp, _ci(nbd), _ci(fx.numel()), _stream_ptr()))
+
+
+def makeabf_bdf(ab1, ab2, ulag, vlag, wlag, f, u, B, rho, dt, ext, bd, nbd):
+    """makeabf + makebdf in one pass over f (b200_makeabf_bdf)."""
+    _, ep = _dv(ext)
+    _, bp = _dv(list(bd) + [0.0] * (4 - len(bd)))
+    l1 = [ulag[0], vlag[0], wlag[0]] if nbd >= 2 else None
+    l2 = [ulag[1], vlag[1], wlag[1]] if nbd >= 3 else None
+    check(_lib.lib().b200_makeabf_bdf(*_p3(ab1), *_p3(ab2), *_p3(l1), *_p3(l2), *_p3(f), *_p3(u), _ptr(B), _cd(rho),
+                                      _cd(dt), ep, bp, _ci(nbd), _ci(f[0].numel()), _stream_ptr()))
+
+
 class steady_simcomp_t:
     """simulation_components/steady_simcomp.f90:49-192 for a list of device fields."""
 

@@ -591,6 +591,59 @@ void orc_linear_advection_dealias(double *fx, double *fy, double *fz,
   dealias_space_free(&sp);
 }
 
+/* ============================ explicit time scheme (Neko rhs_maker, restated) ============== */
+
+void orc_sumab(double *ue, double *ve, double *we, const double *u, const double *v, const double *w,
+               const double *ulag1, const double *vlag1, const double *wlag1,
+               const double *ulag2, const double *vlag2, const double *wlag2,
+               const double ab[3], int nab, int64_t n) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; i++) {
+    ue[i] = ab[0] * u[i] + ab[1] * ulag1[i];
+    ve[i] = ab[0] * v[i] + ab[1] * vlag1[i];
+    we[i] = ab[0] * w[i] + ab[1] * wlag1[i];
+  }
+  if (nab == 3) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+      ue[i] = ue[i] + ab[2] * ulag2[i];
+      ve[i] = ve[i] + ab[2] * vlag2[i];
+      we[i] = we[i] + ab[2] * wlag2[i];
+    }
+  }
+}
+
+void orc_makeabf(double *abx1, double *aby1, double *abz1, double *abx2, double *aby2, double *abz2,
+                 double *fx, double *fy, double *fz, double rho, const double ext[3], int64_t n) {
+  double *l1[3] = {abx1, aby1, abz1}, *l2[3] = {abx2, aby2, abz2}, *f[3] = {fx, fy, fz};
+  for (int c = 0; c < 3; c++) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+      const double ta = ext[1] * l1[c][i] + ext[2] * l2[c][i];
+      l2[c][i] = l1[c][i];
+      l1[c][i] = f[c][i];
+      f[c][i] = (ext[0] * f[c][i] + ta) * rho;
+    }
+  }
+}
+
+void orc_makebdf(const double *ulag1, const double *vlag1, const double *wlag1,
+                 const double *ulag2, const double *vlag2, const double *wlag2,
+                 double *fx, double *fy, double *fz, const double *u, const double *v, const double *w,
+                 const double *B, double rho, double dt, const double bd[4], int nbd, int64_t n) {
+  const double *q[3] = {u, v, w}, *l1[3] = {ulag1, vlag1, wlag1}, *l2[3] = {ulag2, vlag2, wlag2};
+  double *f[3] = {fx, fy, fz};
+  for (int c = 0; c < 3; c++) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+      double tb = q[c][i] * B[i] * bd[1];
+      if (nbd >= 2) tb = tb + l1[c][i] * B[i] * bd[2];
+      if (nbd >= 3) tb = tb + l2[c][i] * B[i] * bd[3];
+      f[c][i] = f[c][i] + tb * (rho / dt);
+    }
+  }
+}
+
 /* ============================ pointwise terms ============================================== */
 
 void orc_ramp(double *chi, const double *rho, int64_t n, double f_min, double f_max, double q,

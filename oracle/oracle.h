@@ -101,6 +101,25 @@ void orc_sensitivity(double *S, const double *u, const double *v, const double *
                      const double *ua, const double *va, const double *wa, double K_obj,
                      int if_lube, int64_t n);
 
+/* ---- explicit time scheme around the RHS (adjoint_pnpn.f90:665-666,688-696) -------------------
+ * The three rhs_maker types live in Neko (src/fluid/rhs_maker*.f90, not vendored); restated from
+ * Neko's published CPU back-end (rhs_maker_cpu.f90), argument order of the reference's call sites.
+ * sumab%compute_fluid: u_e = ab(1)*u + ab(2)*ulag(1) [+ ab(3)*ulag(2) if nab == 3] */
+void orc_sumab(double *ue, double *ve, double *we, const double *u, const double *v, const double *w,
+               const double *ulag1, const double *vlag1, const double *wlag1,
+               const double *ulag2, const double *vlag2, const double *wlag2,
+               const double ab[3], int nab, int64_t n);
+/* makeabf%compute_fluid: ta = ext(2)*f_lag + ext(3)*f_laglag; f_laglag = f_lag; f_lag = f;
+ * f = (ext(1)*f + ta)*rho   (all three components; lag arrays updated in place) */
+void orc_makeabf(double *abx1, double *aby1, double *abz1, double *abx2, double *aby2, double *abz2,
+                 double *fx, double *fy, double *fz, double rho, const double ext[3], int64_t n);
+/* makebdf%compute_fluid: tb = u*B*bd(2) + sum_{ilag=2..nbd} ulag(ilag-1)*B*bd(ilag+1);
+ * f = f + tb*(rho/dt)   (bd has nbd+1 entries; nbd <= 3) */
+void orc_makebdf(const double *ulag1, const double *vlag1, const double *wlag1,
+                 const double *ulag2, const double *vlag2, const double *wlag2,
+                 double *fx, double *fy, double *fz, const double *u, const double *v, const double *w,
+                 const double *B, double rho, double dt, const double bd[4], int nbd, int64_t n);
+
 /* The whole explicit-RHS slice adjoint_pnpn.f90:661-682:
  *   f = 0; brinkman(u_adj, chi); [lube(u_b, chi)]; [f += f_static]; f *= B; adv%compute_adjoint.
  * chi = RAMP(rho) if chi_in == NULL.  sens may be NULL.  lxd == 0 -> no dealias. */

@@ -246,6 +246,33 @@ def adjoint_rhs(v, vb, lx, nelv, D, w, G, B, rho=None, chi=None, fstatic=None, m
     return f, sens, chi_out
 
 
+# ---- explicit time scheme (Neko rhs_maker) ----
+def sumab(u, ulag1, ulag2, ab, nab):
+    out = [np.zeros_like(f64(u[0])) for _ in range(3)]
+    abv = (C.c_double * 3)(*[float(a) for a in ab])
+    lib().orc_sumab(_p(out[0]), _p(out[1]), _p(out[2]), *[_p(f64(a)) for a in u], *[_p(f64(a)) for a in ulag1],
+                    *[_p(f64(a)) for a in ulag2], abv, C.c_int(nab), C.c_int64(out[0].size))
+    return out
+
+
+def makeabf(ab1, ab2, f, rho, ext):
+    """returns (ab1, ab2, f) after the update (copies)."""
+    ab1, ab2, f = [f64(a).copy() for a in ab1], [f64(a).copy() for a in ab2], [f64(a).copy() for a in f]
+    e = (C.c_double * 3)(*[float(a) for a in ext])
+    lib().orc_makeabf(*[_p(a) for a in ab1], *[_p(a) for a in ab2], *[_p(a) for a in f], C.c_double(rho), e,
+                      C.c_int64(f[0].size))
+    return ab1, ab2, f
+
+
+def makebdf(ulag1, ulag2, f, u, B, rho, dt, bd, nbd):
+    f = [f64(a).copy() for a in f]
+    b = (C.c_double * 4)(*[float(a) for a in bd])
+    lib().orc_makebdf(*[_p(f64(a)) for a in ulag1], *[_p(f64(a)) for a in ulag2], *[_p(a) for a in f],
+                      *[_p(f64(a)) for a in u], _p(f64(B)), C.c_double(rho), C.c_double(dt), b, C.c_int(nbd),
+                      C.c_int64(f[0].size))
+    return f
+
+
 # ---- gather-scatter ----
 def gs_classes(key):
     key = np.ascontiguousarray(key, dtype=np.int64)

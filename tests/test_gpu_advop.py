@@ -167,3 +167,43 @@ def test_discrete_adjoint_identity_gpu(dealias):
     nl = np.sqrt(sum((a * a).sum().item() for a in Lv))
     assert nl > 0 and abs(lhs - rhs) / (nw * nl) <= 1e-12
     adv.free()
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_time_scheme_kernels(oracle, order):
+    """sumab / makeabf / makebdf (adjoint_pnpn.f90:665-666,688-696) against the oracle's
+    restatement of Neko's rhs_maker, and the one-pass makeabf+makebdf against the two calls back to back."""
+    ops = _ops()
+    rng = np.random.default_rng(21 + order)
+    n = 3 * 7 ** 3 + 1            # odd length: exercises the tails
+    r3 = lambda: [rng.standard_normal(n) for _ in range(3)]
+    cu = lambda a: [torch.as_tensor(x).cuda() for x in a]
+    u, l1, l2, f0, a1, a2 = r3(), r3(), r3(), r3(), r3(), r3()
+    B = rng.random(n) + 0.5
+    rho, dt = 1.3, 0.0125
+    ab = [3.0, -3.0, 1.0] if order == 3 else [2.0, -1.0, 0.0]
+    bd = [11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0] if order == 3 else [1.5, 2.0, -0.5, 0.0]
+    # sumab
+    ref = oracle.sumab(u, l1, l2, ab, order)
+    ue = [torch.full((n,), float("nan"), device="cuda", dtype=torch.float64) for _ in range(3)]
+    du, dl1, dl2 = cu(u), cu(l1), cu(l2)
+    lag = lambda c: (dl1[c], dl2[c])
+    ops.rhs_maker_sumab_t().compute_fluid(*ue, *du, lag(0), lag(1), lag(2), ab, order)
+    for c in range(3):
+        assert rel_l2(ue[c].cpu().numpy(), ref[c]) <= TOL
+    # makeabf then makebdf
+    ra1, ra2, rf = oracle.makeabf(a1, a2, f0, rho, ab)
+    rf2 = oracle.makebdf(l1, l2, rf, u, B, rho, dt, bd, order)
+    df, da1, da2, dB = cu(f0), cu(a1), cu(a2), torch.as_tensor(B).cuda()
+    ops.rhs_maker_ext_t().compute_fluid(*da1, *da2, *df, rho, ab)
+    for c in range(3):
+        assert rel_l2(df[c].cpu().numpy(), rf[c]) <= TOL
+        assert np.array_equal(da1[c].cpu().numpy(), f0[c]) and np.array_equal(da2[c].cpu().numpy(), a1[c])
+    ops.rhs_maker_bdf_t().compute_fluid(lag(0), lag(1), lag(2), *df, *du, dB, rho, dt, bd, order)
+    for c in range(3):
+        assert rel_l2(df[c].cpu().numpy(), rf2[c]) <= TOL
+    # one pass
+    gf, ga1, ga2 = cu(f0), cu(a1), cu(a2)
+    ops.makeabf_bdf(ga1, ga2, lag(0), lag(1), lag(2), gf, du, dB, rho, dt, ab, bd, order)
+    for c in range(3):
+        assert torch.equal(gf[c], df[c]) and torch.equal(ga1[c], da1[c]) and torch.equal(ga2[c], da2[c])

@@ -272,3 +272,28 @@ def test_golden_fixture(oracle):
     fd = oracle.adjoint_advection_dealias([np.zeros(P.n)] * 3, P.v, P.ub, P.lx, g["lxd"], P.nelv, P.G)
     for c in range(3):
         assert np.allclose(fd[c][idx], g["f_dealias"][c], rtol=1e-11, atol=1e-13)
+
+
+def test_time_scheme_restatement(oracle):
+    """sumab / makeabf / makebdf (Neko rhs_maker, restated in oracle.c) against their defining formulas in
+    numpy, incl. the in-place lag rotation of makeabf and the order-dependent number of BDF terms."""
+    rng = np.random.default_rng(4)
+    n = 1001
+    r3 = lambda: [rng.standard_normal(n) for _ in range(3)]
+    u, l1, l2, f, a1, a2 = r3(), r3(), r3(), r3(), r3(), r3()
+    B = rng.random(n) + 0.5
+    rho, dt = 0.9, 0.02
+    for order, ab, bd in ((2, [2.0, -1.0, 0.0], [1.5, 2.0, -0.5, 0.0]),
+                          (3, [3.0, -3.0, 1.0], [11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0])):
+        ue = oracle.sumab(u, l1, l2, ab, order)
+        for c in range(3):
+            ref = ab[0] * u[c] + ab[1] * l1[c] + (ab[2] * l2[c] if order == 3 else 0.0)
+            assert np.allclose(ue[c], ref, rtol=1e-15, atol=1e-15)
+        n1, n2, nf = oracle.makeabf(a1, a2, f, rho, ab)
+        for c in range(3):
+            assert np.array_equal(n2[c], a1[c]) and np.array_equal(n1[c], f[c])
+            assert np.allclose(nf[c], (ab[0] * f[c] + ab[1] * a1[c] + ab[2] * a2[c]) * rho, rtol=1e-15, atol=1e-15)
+        g = oracle.makebdf(l1, l2, f, u, B, rho, dt, bd, order)
+        for c in range(3):
+            tb = u[c] * B * bd[1] + l1[c] * B * bd[2] + (l2[c] * B * bd[3] if order == 3 else 0.0)
+            assert np.allclose(g[c], f[c] + tb * (rho / dt), rtol=1e-14, atol=1e-14)

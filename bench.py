@@ -86,7 +86,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.05)
 
     def start(self):
         if self.ok:

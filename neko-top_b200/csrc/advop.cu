@@ -13,10 +13,14 @@ template <int LX, int LXD, int MODE>
 cudaError_t launch_one(const AdvLaunch& a) {
   using C = AdvCfg<LX, LXD, MODE>;
   static_assert(C::SMEM <= 227 * 1024, "fine-grid operator exceeds the shared memory of an SM");
-  // as many CTAs per SM as shared memory allows (+1 KB reserved per CTA); cap registers to match
+  // as many CTAs per SM as shared memory allows (+1 KB reserved per CTA); cap registers to match.  The
+  // register file is split over the four schedulers (16384 registers each), so what counts is the number
+  // of warps per scheduler, not the CTA total (ncu r01g: 200 registers x 5 warps allowed ONE CTA per SM).
   constexpr int CTAS = (227 * 1024) / (C::SMEM + 1024) > 0 ? (227 * 1024) / (C::SMEM + 1024) : 1;
-  constexpr int RCAP = 65536 / (C::NTHR * CTAS) / 8 * 8;
-  constexpr int MAXREG = RCAP > 255 ? 255 : (RCAP < (C::NTHR <= 96 ? 224 : 168) ? (C::NTHR <= 96 ? 224 : 168) : RCAP);
+  constexpr int WPS = (C::NTHR / 32 * CTAS + 3) / 4;              // warps per scheduler
+  constexpr int RCAP = 16384 / WPS / 32 / 8 * 8;
+  constexpr int RMIN = (C::NTHR <= 96) ? 224 : 168;
+  constexpr int MAXREG = RCAP > 255 ? 255 : (RCAP < RMIN ? RMIN : RCAP);
   AdvParams<LX, LXD> p;
   memset(&p, 0, sizeof p);
   for (int i = 0; i < LXD * LXD; i++) p.D[i] = a.D[i];
@@ -31,6 +35,8 @@ cudaError_t launch_one(const AdvLaunch& a) {
   static int per_sm = 0;   // per instantiation
   if (!per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHR, C::SMEM);
     if (e != cudaSuccess) return e;

@@ -205,5 +205,6 @@ def test_time_scheme_kernels(oracle, order):
     # one pass
     gf, ga1, ga2 = cu(f0), cu(a1), cu(a2)
     ops.makeabf_bdf(ga1, ga2, lag(0), lag(1), lag(2), gf, du, dB, rho, dt, ab, bd, order)
-    for c in range(3):
-        assert torch.equal(gf[c], df[c]) and torch.equal(ga1[c], da1[c]) and torch.equal(ga2[c], da2[c])
+    for c in range(3):      # (FMA contraction may differ between one and two passes: last-bit differences in f)
+        assert rel_l2(gf[c].cpu().numpy(), rf2[c]) <= TOL
+        assert torch.equal(ga1[c], da1[c]) and torch.equal(ga2[c], da2[c])

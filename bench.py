@@ -266,6 +266,7 @@ def run_b200(args):
     launches = ops.launch_count() - l0
     ms_total = maxr(e0.elapsed_time(e1))
     elem_ms, gs_ms, nmarks = op.get_timing()
+    phases = op.get_phase_timing() if os.environ.get("B200_PHASE_TIMING") else None
     op.enable_timing(False)
     ms_step = ms_total / args.steps
     n_global = sumr(float(n))
@@ -343,6 +344,11 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,
             "clocks": clk.summary(), "checksum_abs_f": checksum,
         }
+        if phases:
+            names = (["boundary_elements", "shared_gs", "pack", "interior_elements", "local_gs", "wait_recv+unpack"]
+                     if os.environ.get("B200_EXCHANGE_OVERLAP") == "elem" else
+                     ["elements", "shared_gs", "pack+exchange_issue", "local_gs", "wait_recv+unpack"])
+            line["phase_ms"] = dict(zip(names, phases))
         print(json.dumps(line), flush=True)
     op.free()
     if N > 1:

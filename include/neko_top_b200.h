@@ -235,6 +235,10 @@ int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, in
  * on the handle's stream when profiling is enabled; used by bench.py's roofline block */
 int b200_adjrhs_enable_timing(void* handle, const int* flag);
 int b200_adjrhs_get_timing(void* handle, double* elem_kernel_ms, double* gs_ms, int64_t* launches);
+/* with environment B200_PHASE_TIMING=1: device time (ms) of the phases of the LAST multi-GPU step --
+ * boundary elements, shared-class gs, pack + exchange issue, interior elements, local gs, unpack;
+ * in: *nphase = capacity of ms[], out: number of phases */
+int b200_adjrhs_get_phase_timing(void* handle, double* ms, int* nphase);
 
 #ifdef __cplusplus
 }

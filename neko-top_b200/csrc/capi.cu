@@ -115,6 +115,7 @@ struct Handle {
   int* d_order = nullptr;
   int gs_mode = 0;                 // 0: CSR kernels (default, fastest), 1: packed class lists, 2: inside the v3 element kernel
   int gs_lag = 2;                  // B200_GS_LAG
+  bool overlap_elem = false;       // B200_EXCHANGE_OVERLAP=elem: overlap the exchange with the interior-element kernel
   int gs_un = 1;                   // classes in flight per thread in gs_op_kernel (B200_GS_UN: 1, 2, 4; measured: 1 is best)
   bool gs_l2hint = true;           // B200_GS_L2HINT=0: no evict_first policy on the streaming inputs
   bool sched_valid = false;
@@ -135,6 +136,9 @@ struct Handle {
   cudaEvent_t ev_done = nullptr;
 
   // timing
+  bool phase_timing = false;      // B200_PHASE_TIMING=1: events between the phases of the last step
+  cudaEvent_t pev[10] = {};
+  int pev_n = 0;
   bool timing = false;
   std::vector<cudaEvent_t> tev;   // pool of (start, mid, end) triples: elem kernel = mid-start, gs = end-mid
   size_t tev_n = 0;               // events of the pool recorded since timing was enabled
@@ -541,6 +545,15 @@ int time_mark(Handle* h) {
   return B200_OK;
 }
 
+// diagnostic: event after phase `idx` of the current step (multi-GPU split path)
+int phase_mark(Handle* h, int idx) {
+  if (!h->phase_timing || idx >= 10) return B200_OK;
+  if (!h->pev[idx]) CK(cudaEventCreate(&h->pev[idx]));
+  CK(cudaEventRecord(h->pev[idx], h->stream));
+  h->pev_n = idx + 1;
+  return B200_OK;
+}
+
 // local gather-scatter launches
 int gs_launch(Handle* h, double* f0, double* f1, double* f2, int nf) {
   if (!h->have_gs) return fail(B200_ERR_STATE, "b200_gs_init not called");
@@ -815,6 +828,10 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   if (g) h->gs_mode = atoi(g) != 0 ? 2 : 1;
   g = getenv("B200_GS_MODE");
   if (g) h->gs_mode = std::min(2, std::max(0, atoi(g)));
+  g = getenv("B200_EXCHANGE_OVERLAP");
+  if (g) h->overlap_elem = (strcmp(g, "elem") == 0);
+  g = getenv("B200_PHASE_TIMING");
+  if (g) h->phase_timing = atoi(g) != 0;
   g = getenv("B200_GS_UN");
   if (g) h->gs_un = atoi(g);
   g = getenv("B200_GS_LAG");
@@ -838,6 +855,7 @@ int b200_adjrhs_free(void** handle) {
   cudaFree(h->d_int_elem);
   for (double* s : h->stage) cudaFree(s);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->pev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_k) cudaEventDestroy(e);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -955,7 +973,44 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
                            chi_out, h->nelv);
   double *f0 = a.f[0], *f1 = a.f[1], *f2 = a.f[2];
   if (int r = time_mark(h)) return r;
-  const bool split = h->comm && h->nshared > 0 && h->nbnd > 0 && h->n_shared_cls >= 0 && h->gs_skip;
+  // Multi-GPU, default: ONE launch over all elements, then the classes holding shared nodes are summed and
+  // packed, and the NCCL exchange runs on the communication stream WHILE the remaining (rank-local) classes
+  // are summed.  The alternative (B200_EXCHANGE_OVERLAP=elem; needs b200_adjrhs_set_boundary_elements)
+  // computes the partition-boundary elements first and overlaps the exchange with the interior-element
+  // kernel; measured on 4 and 8 B200 it loses: the persistent element kernel owns every SM, so it either
+  // delays the NCCL kernel or starts some of its CTAs late behind it (static element partition), and the
+  // element-list variant of the kernel is ~12 % slower than the contiguous one.
+  const bool mgpu = h->comm && h->nshared > 0 && h->n_shared_cls >= 0 && h->gs_skip;
+  if (mgpu && !h->overlap_elem) {
+    if (int r = phase_mark(h, 0)) return r;
+    a.elem_list = h->d_order;
+    if (int r = launch_fused(h, a)) return r;
+    if (int r = masked_lube_post(h, a)) return r;
+    if (int r = phase_mark(h, 1)) return r;
+    if (int r = time_mark(h)) return r;
+    if (h->n_shared_cls > 0) {
+      const int threads = 256, grid = grid_for(h->n_shared_cls, threads, h->num_sm, 4);
+      gs_op_list_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof,
+                                                             h->gs_shared_cls, h->n_shared_cls);
+      LAUNCHED();
+      CK(cudaGetLastError());
+    }
+    if (int r = phase_mark(h, 2)) return r;
+    if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
+    if (int r = phase_mark(h, 3)) return r;
+    if (h->nclass > 0) {
+      const int threads = 256, grid = grid_for(h->nclass, threads, h->num_sm, 8);
+      gs_op_kernel<3, 1><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass,
+                                                           h->gs_skip);
+      LAUNCHED();
+      CK(cudaGetLastError());
+    }
+    if (int r = phase_mark(h, 4)) return r;
+    if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
+    if (int r = phase_mark(h, 5)) return r;
+    return time_mark(h);
+  }
+  const bool split = mgpu && h->nbnd > 0;
   // direct-stiffness summation inside the element kernel (v3, lx = 8) while f is still in L2; the masked
   // lube term is applied by a separate kernel after the element kernel, so it keeps the separate gs pass
   const bool masked_lube = a.sources && h->if_lube && h->lube_mask_size > 0;
@@ -980,8 +1035,10 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     // (with a masked lube term the point-zone kernel must see every element before any summation: no overlap)
     LaunchArgs ab = a;
     if (!masked_lube) { ab.elem_list = h->d_bnd_elem; ab.nelem = h->nbnd; }
+    if (int r = phase_mark(h, 0)) return r;
     if (int r = launch_fused(h, ab)) return r;
     if (int r = masked_lube_post(h, a)) return r;
+    if (int r = phase_mark(h, 1)) return r;
     if (h->n_shared_cls > 0) {
       const int threads = 256, grid = grid_for(h->n_shared_cls, threads, h->num_sm, 4);
       gs_op_list_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof,
@@ -989,9 +1046,12 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
       LAUNCHED();
       CK(cudaGetLastError());
     }
+    if (int r = phase_mark(h, 2)) return r;
     if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
+    if (int r = phase_mark(h, 3)) return r;
     LaunchArgs ai = a; ai.elem_list = h->d_int_elem; ai.nelem = h->nint; ai.gs_in_kernel = fuse_gs;
     if (h->nint > 0 && !masked_lube) if (int r = launch_fused(h, ai)) return r;
+    if (int r = phase_mark(h, 4)) return r;
     if (int r = time_mark(h)) return r;
     if (mode == 2) {
       if (int r = gs_leftover(h, f0, f1, f2)) return r;
@@ -1005,7 +1065,9 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
       LAUNCHED();
       CK(cudaGetLastError());
     }
+    if (int r = phase_mark(h, 5)) return r;
     if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
+    if (int r = phase_mark(h, 6)) return r;
   } else {
     a.elem_list = h->d_order; a.gs_in_kernel = fuse_gs;
     if (int r = launch_fused(h, a)) return r;
@@ -1766,6 +1828,21 @@ int b200_adjrhs_enable_timing(void* handle, const int* flag) {
       h->tev.push_back(e);
     }
   }
+  return B200_OK;
+}
+
+int b200_adjrhs_get_phase_timing(void* handle, double* ms, int* nphase) {
+  if (!handle || !ms || !nphase) return fail(B200_ERR_ARG, "get_phase_timing: null argument");
+  Handle* h = H(handle);
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const int np = h->pev_n > 0 ? h->pev_n - 1 : 0;
+  for (int i = 0; i < np && i < *nphase; i++) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, h->pev[i], h->pev[i + 1]));
+    ms[i] = t;
+  }
+  *nphase = np;
   return B200_OK;
 }
 

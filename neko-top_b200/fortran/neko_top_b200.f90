@@ -164,6 +164,14 @@ module neko_top_b200
        type(c_ptr), value :: fx_d, fy_d, fz_d
      end function b200_adv_linear_dealias_compute
 
+     integer(c_int) function b200_adjrhs_get_phase_timing(handle, ms, nphase) &
+          bind(c, name='b200_adjrhs_get_phase_timing')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       real(c_double), dimension(*) :: ms
+       integer(c_int) :: nphase
+     end function b200_adjrhs_get_phase_timing
+
      integer(c_int) function b200_sumab(ue_d, ve_d, we_d, u_d, v_d, w_d, &
           ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d, ab, nab, n, &
           stream) bind(c, name='b200_sumab')

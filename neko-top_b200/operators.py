@@ -460,6 +460,12 @@ class fused_adjoint_rhs_t:
         check(_lib.lib().b200_adjrhs_get_timing(self._hd.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def get_phase_timing(self):
+        ms = (C.c_double * 10)()
+        n = C.c_int(10)
+        check(_lib.lib().b200_adjrhs_get_phase_timing(self._hd.h, ms, C.byref(n)))
+        return [ms[i] for i in range(n.value)]
+
     def free(self):
         self._hd.free()
 

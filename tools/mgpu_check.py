@@ -51,6 +51,8 @@ def main():
     mk = lambda: [torch.full((n,), float("nan"), device=dev, dtype=torch.float64) for _ in range(3)]
     results = {}
     for mode in ("sequential", "overlap", "overlap_gs1", "overlap_gs2"):
+        # sequential = the default path (exchange overlapped with the local gs); with
+        # B200_EXCHANGE_OVERLAP=elem the "overlap*" modes run the boundary/interior split
         if mode == "overlap":
             op.set_boundary_elements(sh.bnd_elem)
         if mode.startswith("overlap_gs"):      # packed class lists / summation inside the interior kernel

@@ -7,6 +7,7 @@ in bench.py, CPU in the tests); nothing here is inside a timed region.
 Element order inside a brick: e = ex + nex*(ey + ney*ez) (x fastest); points (k, j, i) with i fastest,
 i.e. tensors of shape (nelv, lx, lx, lx) are the Fortran arrays x(lx,lx,lx,nelv).
 """
+import os
 from dataclasses import dataclass, field
 from typing import Tuple
 
@@ -143,6 +144,107 @@ def coords(brick, device="cpu"):
     y = brick.origin[1] + brick.length[1] * Y
     z = brick.origin[2] + brick.length[2] * Z
     return x.contiguous(), y.contiguous(), z.contiguous()
+
+
+# ---- unstructured hexahedral meshes (Neko .nmsh element records) ------------------------------------------
+_LEX2NEK = (0, 1, 3, 2, 4, 5, 7, 6)     # Nek-style cyclic vertex order -> lexicographic (r fastest, then s, t)
+
+
+class HexMesh:
+    """Straight-sided hexahedra given by their eight vertices (ids and coordinates) in the order of a Neko
+    `.nmsh` element record; element and vertex numbering are the file's own.  Produces what the
+    path needs: GLL node coordinates (trilinear map) and a global node key per dof built from the TOPOLOGY
+    (vertex ids), so that coincident nodes of elements with different local orientations get the same key:
+      vertex node   (0, v)                      edge node  (1, v_lo, v_hi, offset from v_lo)
+      face node     (2, sorted 4 vertices -> canonical origin = smallest id, first axis towards the smaller
+                     of its two neighbours, (p, q) in that frame)
+      interior node (3, element, i, j, k)
+    GLL points are symmetric, so an offset m from one end is lx-1-m from the other."""
+
+    def __init__(self, vertex_id, vertex_xyz, lx, name="hexmesh"):
+        self.vid = np.asarray(vertex_id, dtype=np.int64)[:, list(_LEX2NEK)]        # (nelv, 8) lexicographic
+        self.vxyz = np.asarray(vertex_xyz, dtype=np.float64)[:, list(_LEX2NEK), :]
+        self.lx, self.nelv, self.name = int(lx), self.vid.shape[0], name
+        self.n = self.nelv * self.lx ** 3
+        lo, hi = self.vxyz.reshape(-1, 3).min(0), self.vxyz.reshape(-1, 3).max(0)
+        self.origin, self.length = tuple(lo), tuple(hi - lo)
+
+    def coords(self, device="cpu"):
+        lx = self.lx
+        zg, _ = sem.zwgll(lx)
+        t = (zg + 1.0) * 0.5
+        w = np.stack([1.0 - t, t])                                   # w[a, i]: weight of corner a at node i
+        # N[lv, k, j, i] with lv = a + 2b + 4c
+        N = np.einsum("ck,bj,ai->cbakji", w, w, w).reshape(8, lx, lx, lx)
+        xyz = np.einsum("vkji,evd->dekji", N, self.vxyz)
+        return tuple(torch.as_tensor(np.ascontiguousarray(xyz[d]), dtype=torch.float64, device=device) for d in range(3))
+
+    def node_keys(self, device="cpu"):
+        lx, L = self.lx, self.lx - 1
+        rows = np.zeros((self.nelv, lx, lx, lx, 7), dtype=np.int64)
+        k, j, i = np.meshgrid(np.arange(lx), np.arange(lx), np.arange(lx), indexing="ij")
+        idx = np.stack([i, j, k], -1)                                # local (r, s, t) index of every node
+        onb = (idx == 0) | (idx == L)
+        nb = onb.sum(-1)
+        corner = (idx == L).astype(np.int64)                         # corner coordinate where on the boundary
+        for e in range(self.nelv):
+            v = self.vid[e]
+            r = rows[e]
+            # interior
+            m = nb == 0
+            r[m] = np.stack([np.full(m.sum(), 3), np.full(m.sum(), e), i[m], j[m], k[m], 0 * i[m], 0 * i[m]], -1)
+            # vertices
+            m = nb == 3
+            lv = corner[m] @ np.array([1, 2, 4])
+            r[m] = np.stack([0 * lv, v[lv], 0 * lv, 0 * lv, 0 * lv, 0 * lv, 0 * lv], -1)
+            # edges: one free direction d
+            m = nb == 2
+            free = np.argmax(~onb[m], -1)
+            c = corner[m].copy()
+            off = idx[m][np.arange(free.size), free]
+            c[np.arange(free.size), free] = 0
+            va = v[c @ np.array([1, 2, 4])]
+            c[np.arange(free.size), free] = 1
+            vb = v[c @ np.array([1, 2, 4])]
+            swap = va > vb
+            lo_, hi_ = np.where(swap, vb, va), np.where(swap, va, vb)
+            r[m] = np.stack([0 * lo_ + 1, lo_, hi_, np.where(swap, L - off, off), 0 * lo_, 0 * lo_, 0 * lo_], -1)
+            # faces: one fixed direction d, two free directions (d1 < d2)
+            m = nb == 1
+            fixed = np.argmax(onb[m], -1)
+            nn = fixed.size
+            d1 = np.where(fixed == 0, 1, 0)
+            d2 = np.where(fixed == 2, 1, 2)
+            p, q = idx[m][np.arange(nn), d1], idx[m][np.arange(nn), d2]
+            base = corner[m] * 0
+            base[np.arange(nn), fixed] = corner[m][np.arange(nn), fixed]
+            wgt = np.array([1, 2, 4])
+            F = np.zeros((nn, 2, 2), dtype=np.int64)                 # F[a, b]: vertex at (d1 = a, d2 = b)
+            for a in (0, 1):
+                for b in (0, 1):
+                    c = base.copy()
+                    c[np.arange(nn), d1] = a
+                    c[np.arange(nn), d2] = b
+                    F[:, a, b] = v[c @ wgt]
+            flat = F.reshape(nn, 4)
+            o = np.argmin(flat, -1)
+            a0, b0 = o // 2, o % 2
+            na = F[np.arange(nn), 1 - a0, b0]                        # neighbour of the origin along d1
+            nbv = F[np.arange(nn), a0, 1 - b0]                       # ... along d2
+            pp = np.where(a0 == 0, p, L - p)
+            qq = np.where(b0 == 0, q, L - q)
+            first_is_d1 = na < nbv
+            c1, c2 = np.where(first_is_d1, pp, qq), np.where(first_is_d1, qq, pp)
+            sv = np.sort(flat, -1)
+            r[m] = np.stack([0 * c1 + 2, sv[:, 0], sv[:, 1], sv[:, 2], sv[:, 3], c1, c2], -1)
+        _, inv = np.unique(rows.reshape(-1, 7), axis=0, return_inverse=True)
+        return torch.as_tensor(inv.reshape(self.nelv, lx, lx, lx).astype(np.int64), device=device)
+
+
+def load_hex_fixture(path, lx):
+    """tests/golden/debugging_pipe_mesh.npz (made from /root/reference/data/debugging_pipe.nmsh)."""
+    d = np.load(path)
+    return HexMesh(d["vertex_id"], d["vertex_xyz"], lx, name=os.path.basename(path))
 
 
 # ---- deterministic node-keyed pseudo-random numbers (splitmix64) ---------------------------------------

@@ -246,6 +246,14 @@ def test_duct_configs(oracle):
         for k in range(3):
             assert rel_l2(c(f[k]), oracle.gs_add(fo[k], cid, nc)) <= TOL
         assert rel_l2(c(sens), so) <= TOL
+        if lx == 8:      # configs[2] ships `dealias: true` (laminar.case:9-13): lxd = 12
+            op.set_dealias(True)
+            op.step(v, ub, f, chi=chif, sens=sens)
+            fo, so, _ = oracle.adjoint_rhs([c(a) for a in v], [c(a) for a in ub], lx, brick.nelv, sp.dx, sp.wx,
+                                           [c(g) for g in Gf], c(Bf), chi=c(chif), lxd=12)
+            for k in range(3):
+                assert rel_l2(c(f[k]), oracle.gs_add(fo[k], cid, nc)) <= TOL
+            assert rel_l2(c(sens), so) <= TOL
         op.free()
 
 
@@ -385,4 +393,39 @@ def test_step_gs_in_kernel_irregular_classes(oracle):
         for c in range(3):
             assert torch.equal(f[c], g[c])
     _check_step_host(op, v, ub, rho, f, None)
+    op.free()
+
+
+@pytest.mark.parametrize("lx,dealias", [(6, False), (8, False), (6, True)])
+def test_reference_pipe_mesh(oracle, lx, dealias):
+    """SURVEY.md 8d correctness gate: the reference's own mesh fixture data/debugging_pipe.nmsh (160 hexahedra in
+    the file's element/vertex numbering; tests/golden/debugging_pipe_mesh.npz): gather-scatter classes exactly
+    equal to the oracle's, the fused step (GLL and dealiased operator) within 1e-12."""
+    import os
+    from neko_top_b200 import sem, workloads
+    ops = _ops()
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "debugging_pipe_mesh.npz")
+    m = workloads.load_hex_fixture(path, lx)
+    sp = sem.Space(lx)
+    x, y, z = m.coords("cuda")
+    keys = m.node_keys("cuda")
+    G, _, B = sem.geometric_factors(x, y, z, sp)
+    fl = workloads.make_fields(m, x, y, z, keys)
+    flat = lambda a: a.reshape(-1).contiguous()
+    Gf, Bf, v, ub, rho = [flat(g) for g in G], flat(B), [flat(a) for a in fl.v], [flat(a) for a in fl.ub], flat(fl.rho)
+    op = ops.fused_adjoint_rhs_t(ops.coef_t(ops.space_t(lx, sp.dx, sp.wx), m.nelv, Gf, Bf))
+    op.gs.init(flat(keys))
+    if dealias:
+        op.set_dealias(True)
+    c = lambda t: t.cpu().numpy()
+    cid, nc = oracle.gs_classes(c(flat(keys)))
+    gcid, gnc = op.gs.classes()
+    assert gnc == nc and np.array_equal(gcid, cid), "gather-scatter index map differs from the oracle's"
+    f, sens = [_nan(m.n) for _ in range(3)], _nan(m.n)
+    op.step(v, ub, f, rho=rho, sens=sens)
+    fo, so, _ = oracle.adjoint_rhs([c(a) for a in v], [c(a) for a in ub], lx, m.nelv, sp.dx, sp.wx,
+                                   [c(g) for g in Gf], c(Bf), rho=c(rho), lxd=(3 * lx // 2 if dealias else 0))
+    for k in range(3):
+        assert rel_l2(c(f[k]), oracle.gs_add(fo[k], cid, nc)) <= TOL
+    assert rel_l2(c(sens), so) <= TOL
     op.free()

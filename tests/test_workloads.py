@@ -63,3 +63,36 @@ def test_brinkman_zone():
     assert set(np.unique(chi.numpy())) == {0.0, 1000.0}
     inside = chi > 0
     assert float(x[inside].min()) >= 4.75 and float(x[inside].max()) <= 5.25 and float(z[inside].max()) <= 0.0
+
+
+def test_reference_pipe_mesh_fixture():
+    """tests/golden/debugging_pipe_mesh.npz = the hexahedra of /root/reference/data/debugging_pipe.nmsh
+    (160 elements, 275 vertices, 10x4x4 on [0,10]x[-.5,.5]^2, the file's own numbering).  The topological
+    node keys (vertex / edge / face / interior) must induce exactly the partition given by coincident
+    coordinates, the element Jacobians must be positive and the mass matrix must sum to the volume."""
+    import os
+    import numpy as np
+    import torch
+    from neko_top_b200 import sem, workloads
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "debugging_pipe_mesh.npz")
+    raw = np.load(path)
+    assert raw["vertex_id"].shape == (160, 8) and np.unique(raw["vertex_id"]).size == 275
+    if os.path.exists("/root/reference/data/debugging_pipe.nmsh"):      # the fixture is the reference's mesh
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "mk", os.path.join(os.path.dirname(path), "make_pipe_fixture.py"))
+        mk = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mk)
+        vid, xyz = mk.read_nmsh_hexes("/root/reference/data/debugging_pipe.nmsh")
+        assert np.array_equal(vid, raw["vertex_id"]) and np.array_equal(xyz, raw["vertex_xyz"])
+    for lx in (4, 7):
+        m = workloads.load_hex_fixture(path, lx)
+        x, y, z = m.coords()
+        keys = m.node_keys().reshape(-1).numpy()
+        X = np.stack([a.reshape(-1).numpy() for a in (x, y, z)], 1)
+        _, by_coord = np.unique(np.round(X * 1e9).astype(np.int64), axis=0, return_inverse=True)
+        nnode = (10 * (lx - 1) + 1) * (4 * (lx - 1) + 1) ** 2
+        assert np.unique(keys).size == nnode == np.unique(by_coord).size
+        assert np.unique(np.stack([keys, by_coord.reshape(-1)], 1), axis=0).shape[0] == nnode
+        _, jac, B = sem.geometric_factors(x, y, z, sem.Space(lx))
+        assert float(jac.min()) > 0.0 and abs(float(B.sum()) - 10.0) < 1e-12

@@ -162,6 +162,32 @@ int b200_sensitivity(void* sens, const void* u, const void* v, const void* w, co
  * (field_copy), in one pass.  Synchronises the stream (it returns a host scalar). */
 int b200_steady_field_update(double* result, const void* x, void* x_old, const int* n, void* stream);
 
+/* ---- minimum-dissipation objective chain ------------------------------------------
+ * Neko `curl(w1,w2,w3, u1,u2,u3, work1, work2, coef)` as called at
+ * source_terms/adjoint_minimum_dissipation_source_term.f90:231-232: strong derivatives (dudxyz), then
+ * w *= B, gs_op(w, GS_OP_ADD), w *= Binv.  jacinv = coef%jacinv_d, Binv = coef%Binv_d; needs b200_gs_init. */
+int b200_curl(void* handle, void* w1, void* w2, void* w3, const void* u1, const void* u2, const void* u3,
+              const void* jacinv, const void* Binv);
+/* adjoint_minimum_dissipation_source_term_t%compute_ (:175-249): f += obj_scale * curl(curl(u)), restricted to
+ * the 1-based point-zone mask when *mask_size > 0 (mask_exterior_const(., mask, 0) + field_add2s2).
+ * The six scratch fields of :202-209 are owned by the handle. */
+int b200_curlcurl_forcing(void* handle, void* fu, void* fv, void* fw, const void* u, const void* v,
+                          const void* w, const void* jacinv, const void* Binv, const void* mask_d,
+                          const int* mask_size, const double* obj_scale);
+/* minimum_dissipation_objective_function_t%compute (objectives/minimum_dissipation_objective_function.f90:
+ * 186-254), rank-local part (the reference's glsc2 adds an MPI_Allreduce): out3[1] = dissipation =
+ * sum_c |grad u_c|^2 . B, out3[2] = lube_value = ((u+v+w)*chi) . B as written at :230-232 (0 if chi == NULL),
+ * both over the mask if *mask_size > 0; out3[0] = (dissipation + 0.5*K*lube_value)*obj_scale.
+ * Synchronises the handle's stream (host scalars); sums are deterministic. */
+int b200_min_dissipation_objective(void* handle, const void* u, const void* v, const void* w, const void* chi,
+                                   const void* jacinv, const void* mask_d, const int* mask_size,
+                                   const double* K, const double* obj_scale, double* out3);
+/* mask_exterior_const (neko_ext/mask_ops.f90:55-82) on the device -- the reference errors out there
+ * ("GPU not supported for masks yet", :70): fld keeps its values on the 1-based mask, *c elsewhere;
+ * work = scratch field of *n doubles (Neko's scratch registry). */
+int b200_mask_exterior_const(void* fld, void* work, const void* mask_d, const int* mask_size, const double* c,
+                             const int* n, void* stream);
+
 /* ---- explicit time scheme around the RHS (adjoint/adjoint_pnpn.f90:665-666,688-696) --
  * Neko's rhs_maker types, argument order of the reference's call sites; all fields are device pointers of
  * *n doubles; coefficient arrays are HOST pointers.

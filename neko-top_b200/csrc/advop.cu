@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "advop_kernel.cuh"
+#include "deriv_kernels.cuh"
 
 namespace b200 {
 namespace {
@@ -88,7 +89,36 @@ cudaError_t geom_lx(int lxd, const double* J_host, const double* const src[9], d
   return cudaGetLastError();
 }
 
+template <int LX>
+cudaError_t deriv_lx(const DerivLaunch& a) {
+  DerivParams<LX> p;
+  for (int i = 0; i < LX * LX; i++) p.D[i] = a.D[i];
+  for (int c = 0; c < 3; c++) { p.u[c] = a.u[c]; p.out[c] = a.out[c]; }
+  for (int g = 0; g < 9; g++) p.G[g] = a.G[g];
+  p.jacinv = a.jacinv; p.B = a.B; p.nelv = a.nelv;
+  constexpr int NTHR = ((LX * LX + 31) / 32) * 32;
+  const int grid = std::min(a.nelv, a.num_sm * 8);
+  if (grid < 1) return cudaSuccess;
+  if (a.mode == DERIV_CURL_B) deriv_kernel<LX, DERIV_CURL_B><<<grid, NTHR, 0, a.stream>>>(p);
+  else deriv_kernel<LX, DERIV_DISSIPATION><<<grid, NTHR, 0, a.stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+cudaError_t deriv_launch(const DerivLaunch& a, const char** msg) {
+  *msg = nullptr;
+  switch (a.lx) {
+    case 4: return deriv_lx<4>(a);
+    case 5: return deriv_lx<5>(a);
+    case 6: return deriv_lx<6>(a);
+    case 7: return deriv_lx<7>(a);
+    case 8: return deriv_lx<8>(a);
+    case 9: return deriv_lx<9>(a);
+    case 10: return deriv_lx<10>(a);
+    default: *msg = "lx not instantiated (4..10)"; return cudaErrorInvalidValue;
+  }
+}
 
 cudaError_t advop_launch(const AdvLaunch& a, const char** msg) {
   *msg = nullptr;

@@ -34,6 +34,21 @@ cudaError_t advop_launch(const AdvLaunch& a, const char** msg);
 cudaError_t advop_geom_to_fine(int lx, int lxd, const double* J_host, const double* const src[9],
                                double* const dst[9], int nelv, int num_sm, cudaStream_t stream,
                                const char** msg);
+// strong-form derivative operators (deriv_kernels.cuh): mode DERIV_CURL_B -> out[0..2] = B*curl(u);
+// DERIV_DISSIPATION -> out[0] = sum_c |grad u_c|^2
+struct DerivLaunch {
+  int lx, mode, nelv;
+  const double* D;            // HOST, lx*lx column-major
+  const double* u[3];
+  const double* G[9];
+  const double* jacinv;
+  const double* B;
+  double* out[3];
+  int num_sm;
+  cudaStream_t stream;
+};
+cudaError_t deriv_launch(const DerivLaunch& a, const char** msg);
+
 // default fine-grid order of advection_adjoint_factory (adjoint/advection_adjoint_fctry.f90:70,89): 3*lx/2
 inline int advop_default_lxd(int lx) { return 3 * lx / 2; }
 

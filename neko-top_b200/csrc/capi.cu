@@ -24,6 +24,7 @@
 #include "advop.h"
 #include "gs_kernels.cuh"
 #include "pointwise_kernels.cuh"
+#include "deriv_kernels.cuh"
 
 namespace {
 
@@ -128,6 +129,10 @@ struct Handle {
   int64_t sched_nfused = 0;        // classes summed inside the element kernel
   unsigned long long* sched_done = nullptr;
   std::vector<int> sched_elem_last;   // host copy: per position, the last position whose classes touch it (kind 1)
+
+  // minimum-dissipation objective chain: six work fields (curl of curl) and reduction partials
+  double* work6 = nullptr;
+  double* d_partial = nullptr;
 
   // host-staged step
   double* stage[11] = {};
@@ -849,7 +854,7 @@ int b200_adjrhs_free(void** handle) {
   cudaDeviceSynchronize();
   cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep); cudaFree(h->gs_skip);
   cudaFree(h->gs_shared_cls); cudaFree(h->geom_pack); cudaFree(h->G_fine);
-  free_schedule(h); cudaFree(h->d_order);
+  free_schedule(h); cudaFree(h->d_order); cudaFree(h->work6); cudaFree(h->d_partial);
   cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
   cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_bnd_elem);
   cudaFree(h->d_int_elem);
@@ -1334,6 +1339,129 @@ int b200_steady_field_update(double* result, const void* x, void* x_old, const i
   CK(cudaMemcpyAsync(result, d_res, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
   CK(cudaFree(d_res));
+  return B200_OK;
+}
+
+// ---- minimum-dissipation objective chain -------------------------------------------------
+static int deriv_run(Handle* h, int mode, const void* u1, const void* u2, const void* u3, const void* jacinv,
+                     double* o0, double* o1, double* o2) {
+  DerivLaunch L;
+  memset(&L, 0, sizeof L);
+  L.lx = h->lx; L.mode = mode; L.nelv = h->nelv; L.D = h->D;
+  L.u[0] = (const double*)u1; L.u[1] = (const double*)u2; L.u[2] = (const double*)u3;
+  for (int g = 0; g < 9; g++) L.G[g] = h->G[g];
+  L.jacinv = (const double*)jacinv; L.B = h->B;
+  L.out[0] = o0; L.out[1] = o1; L.out[2] = o2;
+  L.num_sm = h->num_sm; L.stream = h->stream;
+  const char* msg = nullptr;
+  cudaError_t e = deriv_launch(L, &msg);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "derivative kernel: %s", msg ? msg : cudaGetErrorString(e));
+  if (h->nelv > 0) LAUNCHED();
+  return B200_OK;
+}
+
+// deterministic local dot product on the handle's stream (synchronises: returns a host scalar)
+static int dot_local(Handle* h, const double* a, const double* b, const int* mask, int mask_size, double* result) {
+  const int nblk = 1024;
+  if (!h->d_partial) if (int r = dmalloc(&h->d_partial, (size_t)nblk)) return r;
+  const int64_t count = mask ? (int64_t)mask_size : h->n;
+  dot_partial_kernel<<<nblk, 256, 0, h->stream>>>(a, b, mask, count, h->d_partial);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  std::vector<double> part(nblk);
+  CK(cudaMemcpyAsync(part.data(), h->d_partial, sizeof(double) * nblk, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double s = 0.0;
+  for (double v : part) s += v;
+  *result = s;
+  return B200_OK;
+}
+
+int b200_curl(void* handle, void* w1, void* w2, void* w3, const void* u1, const void* u2, const void* u3,
+              const void* jacinv, const void* Binv) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!w1 || !w2 || !w3 || !u1 || !u2 || !u3 || !jacinv || !Binv) return fail(B200_ERR_ARG, "curl: null argument");
+  if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
+  if (!h->have_gs) return fail(B200_ERR_STATE, "curl: b200_gs_init not called (Neko's curl averages with gs)");
+  CK(cudaSetDevice(h->device));
+  if (int r = deriv_run(h, DERIV_CURL_B, u1, u2, u3, jacinv, (double*)w1, (double*)w2, (double*)w3)) return r;
+  if (int r = b200_gs_op3(handle, w1, w2, w3)) return r;
+  const int threads = 256;
+  opcolv_kernel<<<grid_for(h->n, threads, h->num_sm, 8), threads, 0, h->stream>>>(
+      (double*)w1, (double*)w2, (double*)w3, (const double*)Binv, h->n);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_curlcurl_forcing(void* handle, void* fu, void* fv, void* fw, const void* u, const void* v,
+                          const void* w, const void* jacinv, const void* Binv, const void* mask_d,
+                          const int* mask_size, const double* obj_scale) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!fu || !fv || !fw || !u || !v || !w || !jacinv || !Binv || !obj_scale)
+    return fail(B200_ERR_ARG, "curlcurl_forcing: null argument");
+  CK(cudaSetDevice(h->device));
+  if (!h->work6 && h->n > 0) if (int r = dmalloc(&h->work6, 6 * (size_t)h->n)) return r;
+  double* wo[6];
+  for (int i = 0; i < 6; i++) wo[i] = h->work6 + (size_t)i * h->n;
+  if (int r = b200_curl(handle, wo[0], wo[1], wo[2], u, v, w, jacinv, Binv)) return r;
+  if (int r = b200_curl(handle, wo[3], wo[4], wo[5], wo[0], wo[1], wo[2], jacinv, Binv)) return r;
+  const int ms = (mask_d && mask_size) ? *mask_size : 0;
+  const int64_t count = ms > 0 ? ms : h->n;
+  const int threads = 256;
+  add2s2_mask3_kernel<<<grid_for(count, threads, h->num_sm, 8), threads, 0, h->stream>>>(
+      (double*)fu, (double*)fv, (double*)fw, wo[3], wo[4], wo[5], *obj_scale, ms > 0 ? (const int*)mask_d : nullptr,
+      count);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_min_dissipation_objective(void* handle, const void* u, const void* v, const void* w, const void* chi,
+                                   const void* jacinv, const void* mask_d, const int* mask_size,
+                                   const double* K, const double* obj_scale, double* out3) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!u || !v || !w || !jacinv || !K || !obj_scale || !out3)
+    return fail(B200_ERR_ARG, "min_dissipation_objective: null argument");
+  if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
+  CK(cudaSetDevice(h->device));
+  if (!h->work6 && h->n > 0) if (int r = dmalloc(&h->work6, 6 * (size_t)h->n)) return r;
+  double* obj = h->work6;
+  const int ms = (mask_d && mask_size) ? *mask_size : 0;
+  const int* mask = ms > 0 ? (const int*)mask_d : nullptr;
+  if (int r = deriv_run(h, DERIV_DISSIPATION, u, v, w, jacinv, obj, nullptr, nullptr)) return r;
+  double diss = 0.0, lube = 0.0;
+  if (int r = dot_local(h, obj, h->B, mask, ms, &diss)) return r;
+  if (chi) {
+    const int threads = 256;
+    lube_density_kernel<<<grid_for(h->n, threads, h->num_sm, 8), threads, 0, h->stream>>>(
+        obj, (const double*)u, (const double*)v, (const double*)w, (const double*)chi, h->n);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (int r = dot_local(h, obj, h->B, mask, ms, &lube)) return r;
+  }
+  out3[1] = diss; out3[2] = lube;
+  out3[0] = (diss + (chi ? 0.5 * (*K) * lube : 0.0)) * (*obj_scale);
+  return B200_OK;
+}
+
+int b200_mask_exterior_const(void* fld, void* work, const void* mask_d, const int* mask_size, const double* c,
+                             const int* n, void* stream) {
+  if (!fld || !work || !mask_d || !mask_size || !c || !n) return fail(B200_ERR_ARG, "mask_exterior_const: null argument");
+  const int threads = 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  fill_kernel<<<grid_for(*n, threads, dev_sm_count(), 8), threads, 0, st>>>((double*)work, *c, (int64_t)*n);
+  LAUNCHED();
+  if (*mask_size > 0) {
+    copy_mask_kernel<<<grid_for(*mask_size, threads, dev_sm_count(), 8), threads, 0, st>>>(
+        (double*)work, (const double*)fld, (const int*)mask_d, *mask_size);
+    LAUNCHED();
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(fld, work, sizeof(double) * (size_t)*n, cudaMemcpyDeviceToDevice, st));
   return B200_OK;
 }
 

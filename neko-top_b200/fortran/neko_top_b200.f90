@@ -172,6 +172,44 @@ module neko_top_b200
        integer(c_int) :: nphase
      end function b200_adjrhs_get_phase_timing
 
+     integer(c_int) function b200_curl(handle, w1_d, w2_d, w3_d, u1_d, u2_d, &
+          u3_d, jacinv_d, Binv_d) bind(c, name='b200_curl')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: w1_d, w2_d, w3_d, u1_d, u2_d, u3_d, jacinv_d, Binv_d
+     end function b200_curl
+
+     integer(c_int) function b200_curlcurl_forcing(handle, fu_d, fv_d, fw_d, &
+          u_d, v_d, w_d, jacinv_d, Binv_d, mask_d, mask_size, obj_scale) &
+          bind(c, name='b200_curlcurl_forcing')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: fu_d, fv_d, fw_d, u_d, v_d, w_d, jacinv_d, Binv_d
+       type(c_ptr), value :: mask_d
+       integer(c_int) :: mask_size
+       real(c_double) :: obj_scale
+     end function b200_curlcurl_forcing
+
+     integer(c_int) function b200_min_dissipation_objective(handle, u_d, v_d, &
+          w_d, chi_d, jacinv_d, mask_d, mask_size, K, obj_scale, out3) &
+          bind(c, name='b200_min_dissipation_objective')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: u_d, v_d, w_d, chi_d, jacinv_d, mask_d
+       integer(c_int) :: mask_size
+       real(c_double) :: K, obj_scale
+       real(c_double), dimension(3) :: out3
+     end function b200_min_dissipation_objective
+
+     integer(c_int) function b200_mask_exterior_const(fld_d, work_d, mask_d, &
+          mask_size, c, n, stream) bind(c, name='b200_mask_exterior_const')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: fld_d, work_d, mask_d
+       integer(c_int) :: mask_size, n
+       real(c_double) :: c
+       type(c_ptr), value :: stream
+     end function b200_mask_exterior_const
+
      integer(c_int) function b200_sumab(ue_d, ve_d, we_d, u_d, v_d, w_d, &
           ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d, ab, nab, n, &
           stream) bind(c, name='b200_sumab')

@@ -255,6 +255,43 @@ def compute_sensitivity(sens, u, v, w, u_adj, v_adj, w_adj, K_obj=1.0, if_lube=T
                                       _ptr(w_adj), _cd(K_obj), _ci(if_lube), _ci(sens.numel()), _stream_ptr()))
 
 
+# ---- minimum-dissipation objective chain -------------------------------------------------------------------
+def curl(handle, w, u, jacinv, Binv):
+    """Neko curl(w1,w2,w3, u1,u2,u3, ., ., coef): strong curl, x B, gs_op(ADD), x Binv.  handle: a
+    fused_adjoint_rhs_t (its gs must be initialised)."""
+    check(_lib.lib().b200_curl(handle.handle.h, *[_ptr(a) for a in w], *[_ptr(a) for a in u], _ptr(jacinv), _ptr(Binv)))
+
+
+class adjoint_minimum_dissipation_source_term_t:
+    """source_terms/adjoint_minimum_dissipation_source_term.f90:52-249: f += obj_scale * curl(curl(u))."""
+
+    def init_from_components(self, f_x, f_y, f_z, u, v, w, obj_scale, mask, if_mask, coef, handle, Binv):
+        self.fields, self.u, self.v, self.w = (f_x, f_y, f_z), u, v, w
+        self.obj_scale, self.mask, self.coef, self.handle, self.Binv = float(obj_scale), (mask if if_mask else None), coef, handle, Binv
+
+    def compute_(self, t=0.0, tstep=0):
+        ms = 0 if self.mask is None else self.mask.numel()
+        check(_lib.lib().b200_curlcurl_forcing(self.handle.handle.h, *[_ptr(a) for a in self.fields], _ptr(self.u),
+                                               _ptr(self.v), _ptr(self.w), _ptr(self.coef.jacinv), _ptr(self.Binv),
+                                               _ptr(self.mask), _ci(ms), _cd(self.obj_scale)))
+
+
+def min_dissipation_objective(handle, u, v, w, chi, jacinv, mask=None, K=1.0, obj_scale=1.0):
+    """minimum_dissipation_objective_function_t%compute (:186-254), rank-local: (objective, dissipation, lube)."""
+    out = (C.c_double * 3)()
+    ms = 0 if mask is None else mask.numel()
+    check(_lib.lib().b200_min_dissipation_objective(handle.handle.h, _ptr(u), _ptr(v), _ptr(w), _ptr(chi), _ptr(jacinv),
+                                                    _ptr(mask), _ci(ms), _cd(K), _cd(obj_scale), out))
+    return out[0], out[1], out[2]
+
+
+def mask_exterior_const(fld, mask, const):
+    """neko_ext/mask_ops.f90:55-82 on the device."""
+    work = torch.empty_like(fld)
+    check(_lib.lib().b200_mask_exterior_const(_ptr(fld), _ptr(work), _ptr(mask), _ci(mask.numel()), _cd(const),
+                                              _ci(fld.numel()), _stream_ptr()))
+
+
 # ---- explicit time scheme around the RHS (Neko rhs_maker types; adjoint_pnpn.f90:665-666,688-696) ---------
 def _dv(a):
     v = np.ascontiguousarray(a, dtype=np.float64)

@@ -591,6 +591,111 @@ void orc_linear_advection_dealias(double *fx, double *fy, double *fz,
   dealias_space_free(&sp);
 }
 
+/* ============================ minimum-dissipation objective chain ========================== */
+
+void orc_dudxyz(double *du, const double *u, const double *dr, const double *ds, const double *dt,
+                const double *jacinv, int lx, int nelv, const double *D) {
+  size_t N = (size_t)lx * lx * lx;
+#pragma omp parallel
+  {
+    double *ur = (double *)malloc(sizeof(double) * 3 * N), *us = ur + N, *ut = us + N;
+#pragma omp for schedule(static)
+    for (int e = 0; e < nelv; e++) {
+      size_t o = N * e;
+      local_grad(ur, us, ut, u + o, D, lx);
+      for (size_t i = 0; i < N; i++)
+        du[o + i] = jacinv[o + i] * (dr[o + i] * ur[i] + ds[o + i] * us[i] + dt[o + i] * ut[i]);
+    }
+    free(ur);
+  }
+}
+
+void orc_curl(double *w1, double *w2, double *w3, const double *u1, const double *u2, const double *u3,
+              int lx, int nelv, const double *D, double *const G[9], const double *jacinv,
+              const double *B, const double *Binv, const int64_t *class_id, int64_t nclass) {
+  size_t n = (size_t)lx * lx * lx * nelv;
+  double *a = (double *)malloc(sizeof(double) * n), *b = (double *)malloc(sizeof(double) * n);
+  /* G[0..8] = drdx,dsdx,dtdx, drdy,dsdy,dtdy, drdz,dsdz,dtdz */
+  orc_dudxyz(a, u3, G[3], G[4], G[5], jacinv, lx, nelv, D);   /* dw/dy */
+  orc_dudxyz(b, u2, G[6], G[7], G[8], jacinv, lx, nelv, D);   /* dv/dz */
+  for (size_t i = 0; i < n; i++) w1[i] = a[i] - b[i];
+  orc_dudxyz(a, u1, G[6], G[7], G[8], jacinv, lx, nelv, D);   /* du/dz */
+  orc_dudxyz(b, u3, G[0], G[1], G[2], jacinv, lx, nelv, D);   /* dw/dx */
+  for (size_t i = 0; i < n; i++) w2[i] = a[i] - b[i];
+  orc_dudxyz(a, u2, G[0], G[1], G[2], jacinv, lx, nelv, D);   /* dv/dx */
+  orc_dudxyz(b, u1, G[3], G[4], G[5], jacinv, lx, nelv, D);   /* du/dy */
+  for (size_t i = 0; i < n; i++) w3[i] = a[i] - b[i];
+  free(a); free(b);
+  double *W[3] = {w1, w2, w3};
+  for (int c = 0; c < 3; c++) {
+    for (size_t i = 0; i < n; i++) W[c][i] *= B[i];
+    orc_gs_add(W[c], class_id, nclass, (int64_t)n);
+    for (size_t i = 0; i < n; i++) W[c][i] *= Binv[i];
+  }
+}
+
+void orc_mask_exterior_const(double *fld, const int *mask, int mask_size, double c, int64_t n) {
+  double *work = (double *)malloc(sizeof(double) * (size_t)n);
+  for (int64_t i = 0; i < n; i++) work[i] = c;
+  for (int m = 0; m < mask_size; m++) work[mask[m] - 1] = fld[mask[m] - 1];
+  memcpy(fld, work, sizeof(double) * (size_t)n);
+  free(work);
+}
+
+double orc_glsc2_mask(const double *a, const double *b, const int *mask, int mask_size, int64_t n) {
+  double s = 0.0;
+  if (mask) { for (int m = 0; m < mask_size; m++) s += a[mask[m] - 1] * b[mask[m] - 1]; }
+  else { for (int64_t i = 0; i < n; i++) s += a[i] * b[i]; }
+  return s;
+}
+
+void orc_curlcurl_forcing(double *fu, double *fv, double *fw, const double *u, const double *v,
+                          const double *w, int lx, int nelv, const double *D, double *const G[9],
+                          const double *jacinv, const double *B, const double *Binv,
+                          const int64_t *class_id, int64_t nclass, const int *mask, int mask_size,
+                          double obj_scale) {
+  size_t n = (size_t)lx * lx * lx * nelv;
+  double *wo = (double *)malloc(sizeof(double) * 6 * n);
+  double *o1 = wo, *o2 = wo + n, *o3 = wo + 2 * n, *o4 = wo + 3 * n, *o5 = wo + 4 * n, *o6 = wo + 5 * n;
+  orc_curl(o1, o2, o3, u, v, w, lx, nelv, D, G, jacinv, B, Binv, class_id, nclass);       /* :231 */
+  orc_curl(o4, o5, o6, o1, o2, o3, lx, nelv, D, G, jacinv, B, Binv, class_id, nclass);    /* :232 */
+  if (mask) {                                                                             /* :235-239 */
+    orc_mask_exterior_const(o4, mask, mask_size, 0.0, (int64_t)n);
+    orc_mask_exterior_const(o5, mask, mask_size, 0.0, (int64_t)n);
+    orc_mask_exterior_const(o6, mask, mask_size, 0.0, (int64_t)n);
+  }
+  for (size_t i = 0; i < n; i++) {                                                        /* :241-243 */
+    fu[i] = fu[i] + obj_scale * o4[i];
+    fv[i] = fv[i] + obj_scale * o5[i];
+    fw[i] = fw[i] + obj_scale * o6[i];
+  }
+  free(wo);
+}
+
+double orc_min_dissipation_objective(double out[2], const double *u, const double *v, const double *w,
+                                     const double *chi, int lx, int nelv, const double *D,
+                                     double *const G[9], const double *jacinv, const double *B,
+                                     const int *mask, int mask_size, double K, double obj_scale) {
+  size_t n = (size_t)lx * lx * lx * nelv;
+  double *obj = (double *)calloc(n, sizeof(double)), *g = (double *)malloc(sizeof(double) * n);
+  const double *U[3] = {u, v, w};
+  for (int c = 0; c < 3; c++)            /* :200-213 grad = dudxyz in x, y, z */
+    for (int d = 0; d < 3; d++) {
+      orc_dudxyz(g, U[c], G[3 * d], G[3 * d + 1], G[3 * d + 2], jacinv, lx, nelv, D);
+      for (size_t i = 0; i < n; i++) obj[i] += g[i] * g[i];
+    }
+  out[0] = orc_glsc2_mask(obj, B, mask, mask_size, (int64_t)n);                           /* :217-222 */
+  out[1] = 0.0;
+  if (chi) {   /* :230-239 -- as written: col3(obj,u,chi); addcol3(obj,v,chi); addcol3(obj,w,chi) = (u+v+w)*chi */
+    for (size_t i = 0; i < n; i++) obj[i] = u[i] * chi[i];
+    for (size_t i = 0; i < n; i++) obj[i] += v[i] * chi[i];
+    for (size_t i = 0; i < n; i++) obj[i] += w[i] * chi[i];
+    out[1] = orc_glsc2_mask(obj, B, mask, mask_size, (int64_t)n);
+  }
+  free(obj); free(g);
+  return (out[0] + (chi ? 0.5 * K * out[1] : 0.0)) * obj_scale;
+}
+
 /* ============================ explicit time scheme (Neko rhs_maker, restated) ============== */
 
 void orc_sumab(double *ue, double *ve, double *we, const double *u, const double *v, const double *w,

@@ -101,6 +101,36 @@ void orc_sensitivity(double *S, const double *u, const double *v, const double *
                      const double *ua, const double *va, const double *wa, double K_obj,
                      int if_lube, int64_t n);
 
+/* ---- minimum-dissipation objective chain -------------------------------------------
+ * Neko operators restated from their published CPU back-end (operators.f90 / opr_cpu_*; not vendored):
+ * dudxyz: du = jacinv * (dr*ur + ds*us + dt*ut)  (strong derivative in one physical direction) */
+void orc_dudxyz(double *du, const double *u, const double *dr, const double *ds, const double *dt,
+                const double *jacinv, int lx, int nelv, const double *D);
+/* curl(w, u): strong curl, then mass-weighted averaging over coincident nodes:
+ *   w1 = du3/dy - du2/dz, w2 = du1/dz - du3/dx, w3 = du2/dx - du1/dy; w *= B; gs_op(w, ADD); w *= Binv
+ * (Binv = 1/gs(B), coef_t).  class_id/nclass: orc_gs_classes of the mesh. */
+void orc_curl(double *w1, double *w2, double *w3, const double *u1, const double *u2, const double *u3,
+              int lx, int nelv, const double *D, double *const G[9], const double *jacinv,
+              const double *B, const double *Binv, const int64_t *class_id, int64_t nclass);
+/* mask_ops.f90:55-82 mask_exterior_const: keep fld on the 1-based mask indices, `c` elsewhere */
+void orc_mask_exterior_const(double *fld, const int *mask, int mask_size, double c, int64_t n);
+/* math_ext.f90:99-116 glsc2_mask (local part): sum_{i in mask} a_i*b_i; mask == NULL -> glsc2 */
+double orc_glsc2_mask(const double *a, const double *b, const int *mask, int mask_size, int64_t n);
+/* adjoint_minimum_dissipation_source_term.f90:175-249: f += obj_scale * curl(curl(u)) [masked] */
+void orc_curlcurl_forcing(double *fu, double *fv, double *fw, const double *u, const double *v,
+                          const double *w, int lx, int nelv, const double *D, double *const G[9],
+                          const double *jacinv, const double *B, const double *Binv,
+                          const int64_t *class_id, int64_t nclass, const int *mask, int mask_size,
+                          double obj_scale);
+/* minimum_dissipation_objective_function.f90:186-254: out[0] = dissipation = sum |grad u_c|^2 * B,
+ * out[1] = lube_value = sum (u+v+w)*chi * B -- what :230-232 literally computes (col3/addcol3 with the
+ * velocity components, not their squares; restated as written) -- 0 if chi == NULL; both over the mask if given;
+ * returns the objective (dissipation + 0.5*K*lube_value)*obj_scale */
+double orc_min_dissipation_objective(double out[2], const double *u, const double *v, const double *w,
+                                     const double *chi, int lx, int nelv, const double *D,
+                                     double *const G[9], const double *jacinv, const double *B,
+                                     const int *mask, int mask_size, double K, double obj_scale);
+
 /* ---- explicit time scheme around the RHS (adjoint_pnpn.f90:665-666,688-696) -------------------
  * The three rhs_maker types live in Neko (src/fluid/rhs_maker*.f90, not vendored); restated from
  * Neko's published CPU back-end (rhs_maker_cpu.f90), argument order of the reference's call sites.

@@ -246,6 +246,51 @@ def adjoint_rhs(v, vb, lx, nelv, D, w, G, B, rho=None, chi=None, fstatic=None, m
     return f, sens, chi_out
 
 
+# ---- minimum-dissipation objective chain ----
+def _mask(mask):
+    if mask is None:
+        return None, 0
+    m = np.ascontiguousarray(mask, dtype=np.int32)
+    return m, m.size
+
+
+def curl(u, lx, nelv, D, G, jacinv, B, Binv, cid, nclass):
+    n = lx ** 3 * nelv
+    w = [np.zeros(n) for _ in range(3)]
+    lib().orc_curl(*[_p(a) for a in w], *[_p(f64(a)) for a in u], C.c_int(lx), C.c_int(nelv), _p(_colmajor(D)),
+                   _G(G), _p(f64(jacinv)), _p(f64(B)), _p(f64(Binv)), cid.ctypes.data_as(_lp), C.c_int64(nclass))
+    return w
+
+
+def curlcurl_forcing(f, u, lx, nelv, D, G, jacinv, B, Binv, cid, nclass, mask=None, obj_scale=1.0):
+    f = [f64(a).copy() for a in f]
+    m, ms = _mask(mask)
+    lib().orc_curlcurl_forcing(*[_p(a) for a in f], *[_p(f64(a)) for a in u], C.c_int(lx), C.c_int(nelv),
+                               _p(_colmajor(D)), _G(G), _p(f64(jacinv)), _p(f64(B)), _p(f64(Binv)),
+                               cid.ctypes.data_as(_lp), C.c_int64(nclass),
+                               m.ctypes.data_as(_ip) if m is not None else None, C.c_int(ms), C.c_double(obj_scale))
+    return f
+
+
+def min_dissipation_objective(u, chi, lx, nelv, D, G, jacinv, B, mask=None, K=1.0, obj_scale=1.0):
+    """returns (objective, dissipation, lube_value)."""
+    out = (C.c_double * 2)()
+    m, ms = _mask(mask)
+    lib().orc_min_dissipation_objective.restype = C.c_double
+    val = lib().orc_min_dissipation_objective(out, *[_p(f64(a)) for a in u], _p(f64(chi)) if chi is not None else None,
+                                              C.c_int(lx), C.c_int(nelv), _p(_colmajor(D)), _G(G), _p(f64(jacinv)),
+                                              _p(f64(B)), m.ctypes.data_as(_ip) if m is not None else None,
+                                              C.c_int(ms), C.c_double(K), C.c_double(obj_scale))
+    return val, out[0], out[1]
+
+
+def mask_exterior_const(fld, mask, c):
+    fld = f64(fld).copy()
+    m, ms = _mask(mask)
+    lib().orc_mask_exterior_const(_p(fld), m.ctypes.data_as(_ip), C.c_int(ms), C.c_double(c), C.c_int64(fld.size))
+    return fld
+
+
 # ---- explicit time scheme (Neko rhs_maker) ----
 def sumab(u, ulag1, ulag2, ab, nab):
     out = [np.zeros_like(f64(u[0])) for _ in range(3)]

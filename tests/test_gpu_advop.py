@@ -208,3 +208,52 @@ def test_time_scheme_kernels(oracle, order):
     for c in range(3):      # (FMA contraction may differ between one and two passes: last-bit differences in f)
         assert rel_l2(gf[c].cpu().numpy(), rf2[c]) <= TOL
         assert torch.equal(ga1[c], da1[c]) and torch.equal(ga2[c], da2[c])
+
+
+@pytest.mark.parametrize("lx", [5, 8])
+def test_min_dissipation_chain(oracle, lx):
+    """Neko curl (strong curl, B, gs, Binv), the curl-curl forcing of
+    adjoint_minimum_dissipation_source_term.f90:231-243 with and without a point-zone mask, the objective of
+    minimum_dissipation_objective_function.f90:186-254 and mask_exterior_const on the device."""
+    ops = _ops()
+    P = Problem(lx, ne=(3, 2, 2), deform=0.03)
+    keys = P.keys.reshape(-1).numpy()
+    cid, nc = oracle.gs_classes(keys)
+    Bsum = oracle.gs_add(P.B, cid, nc)
+    Binv, jacinv = 1.0 / Bsum, 1.0 / P.jac
+    coef = _coef(P, with_jacinv=True)
+    op = ops.fused_adjoint_rhs_t(coef)
+    op.gs.init(P.keys.reshape(-1).cuda())
+    dBinv = torch.as_tensor(Binv).cuda()
+    u = P.cuda("ub")
+    # curl
+    wref = oracle.curl(P.ub, lx, P.nelv, P.D, P.G, jacinv, P.B, Binv, cid, nc)
+    w = [_nan(P.n) for _ in range(3)]
+    ops.curl(op, w, u, coef.jacinv, dBinv)
+    for c in range(3):
+        assert rel_l2(w[c].cpu().numpy(), wref[c]) <= TOL
+    # curl-curl forcing, unmasked and masked
+    rng = np.random.default_rng(9)
+    f0 = [rng.standard_normal(P.n) for _ in range(3)]
+    mask = (np.sort(rng.choice(P.n, P.n // 5, replace=False)) + 1).astype(np.int32)
+    dmask = torch.as_tensor(mask).cuda()
+    for mk, dm in ((None, None), (mask, dmask)):
+        ref = oracle.curlcurl_forcing(f0, P.ub, lx, P.nelv, P.D, P.G, jacinv, P.B, Binv, cid, nc, mask=mk, obj_scale=0.7)
+        f = [torch.as_tensor(a).cuda() for a in f0]
+        st = ops.adjoint_minimum_dissipation_source_term_t()
+        st.init_from_components(*f, *u, 0.7, dm, dm is not None, coef, op, dBinv)
+        st.compute_()
+        for c in range(3):
+            assert rel_l2(f[c].cpu().numpy(), ref[c]) <= TOL
+    # objective
+    chi = rng.random(P.n) * 1000.0
+    for mk, dm in ((None, None), (mask, dmask)):
+        ref = oracle.min_dissipation_objective(P.ub, chi, lx, P.nelv, P.D, P.G, jacinv, P.B, mask=mk, K=2.0, obj_scale=0.5)
+        got = ops.min_dissipation_objective(op, *u, torch.as_tensor(chi).cuda(), coef.jacinv, mask=dm, K=2.0, obj_scale=0.5)
+        for a, b in zip(got, ref):
+            assert abs(a - b) <= 1e-12 * max(1.0, abs(b))
+    # mask_exterior_const
+    fld = torch.as_tensor(f0[0]).cuda()
+    ops.mask_exterior_const(fld, dmask, -3.5)
+    assert np.array_equal(fld.cpu().numpy(), oracle.mask_exterior_const(f0[0], mask, -3.5))
+    op.free()

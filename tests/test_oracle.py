@@ -297,3 +297,29 @@ def test_time_scheme_restatement(oracle):
         for c in range(3):
             tb = u[c] * B * bd[1] + l1[c] * B * bd[2] + (l2[c] * B * bd[3] if order == 3 else 0.0)
             assert np.allclose(g[c], f[c] + tb * (rho / dt), rtol=1e-14, atol=1e-14)
+
+
+def test_objective_chain_restatement(oracle):
+    """Neko curl / dudxyz / objective restated in oracle.c against closed forms on an affine mesh: the curl of a
+    rigid rotation is (0,0,2), curl(curl(u)) of a divergence-free harmonic-like field is -laplace(u), the
+    dissipation of u = (sin 2y, 0, 0) on the unit cube is 4(1/2 + sin(4)/8); mask semantics of
+    mask_exterior_const / glsc2_mask (1-based indices)."""
+    from helpers import Problem
+    lx = 8
+    P = Problem(lx, ne=(2, 2, 2), deform=0.0)
+    x, y, z = [a.reshape(-1).numpy() for a in P.xyz]
+    cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
+    Binv, jacinv = 1.0 / oracle.gs_add(P.B, cid, nc), 1.0 / P.jac
+    w = oracle.curl([-y, x, 0 * x], lx, P.nelv, P.D, P.G, jacinv, P.B, Binv, cid, nc)
+    assert np.abs(w[0]).max() < 1e-12 and np.abs(w[1]).max() < 1e-12 and np.abs(w[2] - 2.0).max() < 1e-12
+    # u = (sin(y) , 0, 0): div u = 0, curl curl u = -laplace u = (sin y, 0, 0)
+    f = oracle.curlcurl_forcing([0 * x] * 3, [np.sin(y), 0 * x, 0 * x], lx, P.nelv, P.D, P.G, jacinv, P.B, Binv,
+                                cid, nc, obj_scale=2.0)
+    assert np.abs(f[0] - 2.0 * np.sin(y)).max() < 1e-6 and np.abs(f[1]).max() < 1e-8 and np.abs(f[2]).max() < 1e-8
+    val, dis, lube = oracle.min_dissipation_objective([np.sin(2 * y), 0 * x, 0 * x], None, lx, P.nelv, P.D, P.G,
+                                                      jacinv, P.B, obj_scale=3.0)
+    exact = 4.0 * (0.5 + np.sin(4.0) / 8.0)
+    assert abs(dis - exact) < 1e-9 and lube == 0.0 and abs(val - 3.0 * dis) < 1e-14
+    mask = np.array([1, 5, P.n], dtype=np.int32)
+    g = oracle.mask_exterior_const(x + 1.0, mask, -1.0)
+    assert g[0] == x[0] + 1.0 and g[4] == x[4] + 1.0 and g[-1] == x[-1] + 1.0 and np.all(np.delete(g, [0, 4, P.n - 1]) == -1.0)

@@ -62,6 +62,7 @@ struct KParams2 {
   const int4* gs_hex;         // 9..16 members, 4 x int4 per class
   unsigned long long* gs_done;  // one counter per window of nslots consecutive positions (zeroed per launch)
   int gs_lag;                 // windows between storing an element and summing its classes (>= 1)
+  int elem_base;              // v2: added to every element index (field pointers stay 16-byte aligned for odd LX)
 };
 
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
@@ -97,10 +98,19 @@ struct V2Cfg {
   static constexpr int NTHREADS = NE * NCTHR + 32;
   static constexpr int PLANE = LX * LX;                    // doubles
   static constexpr int PLANE_BYTES = PLANE * 8;
-  static constexpr bool BULK = (PLANE_BYTES % 16 == 0);    // even LX: 1-D TMA; odd LX: 8-byte cp.async
+  // Odd LX: a k-plane of a user field (LX*LX*8 bytes, = 8 mod 16) starts on a 16-byte boundary only for every
+  // other (element, plane) pair, and TMA bulk copies need 16-byte aligned source, destination and size.  The
+  // producer therefore copies the aligned WINDOW of FS = PLANE_BYTES + 8 bytes that contains the plane
+  // (starting 8 bytes early when (e + k) is odd) and the consumers read at the matching 8-byte shift.  The
+  // window never leaves the 16-byte granule of the plane's first/last double, so it stays inside the field's
+  // allocation (at most 8 bytes of a neighbouring plane, or of the granule's tail at the very end of the
+  // array, are read and ignored).  The packed geometry block (10 planes = a multiple of 80 bytes) is aligned
+  // for every LX.
+  static constexpr bool ODD = (LX % 2 == 1);
+  static constexpr int FS = ODD ? PLANE_BYTES + 8 : PLANE_BYTES;   // bytes copied per user-field plane
   static constexpr int al(int x) { return (x + 127) & ~127; }
   static constexpr int W_BYTES = al(6 * N * 8);
-  static constexpr int STAGE_BYTES = al(NF * PLANE_BYTES);
+  static constexpr int STAGE_BYTES = al(NGEO * PLANE_BYTES + (NF - NGEO) * FS);
   static constexpr int SLOT_BYTES = W_BYTES + NS * STAGE_BYTES;
   static constexpr int BAR_OFF = NE * SLOT_BYTES;
   static constexpr int SMEM = BAR_OFF + 8 * 2 * NE * NS + 16;
@@ -137,8 +147,7 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    const uint32_t full_cnt = C::BULK ? 1u : 32u;
-    for (int i = 0; i < NE * NS; i++) { mbar_init(&bars[2 * i], full_cnt); mbar_init(&bars[2 * i + 1], C::NCWARP); }
+    for (int i = 0; i < NE * NS; i++) { mbar_init(&bars[2 * i], 1u); mbar_init(&bars[2 * i + 1], C::NCWARP); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -160,7 +169,7 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
       it[s] = 0; kk[s] = 0; st[s] = 0; ph[s] = 0;
       remaining += (nmy[s] > 0);
     }
-    const uint32_t stage_tx = (uint32_t)p.n_active * C::PLANE_BYTES;
+    const uint32_t stage_tx = (uint32_t)(NGEO * C::PLANE_BYTES + (p.n_active - NGEO) * C::FS);
     while (remaining > 0) {
       bool progressed = false;
 #pragma unroll
@@ -172,40 +181,30 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
         progressed = true;
         int e = (int)blockIdx.x * NE + s + it[s] * nslots;
         if (p.elem_list) e = __ldg(p.elem_list + e);
+        e += p.elem_base;
         const size_t goff = (size_t)e * N + (size_t)kk[s] * PLANE;
+        // odd LX: start the user-field window one double early when the plane is not 16-byte aligned
+        const size_t uoff = C::ODD ? (goff & ~(size_t)1) : goff;
         unsigned char* dst = smem + s * C::SLOT_BYTES + C::W_BYTES + st[s] * C::STAGE_BYTES;
-        if constexpr (C::BULK) {
-          if (elect_one()) {
-            mbar_expect_tx(full, stage_tx);
-            tma_load_1d(dst, p.geom + goff * NGEO, NGEO * C::PLANE_BYTES, full);
+        if (elect_one()) {
+          mbar_expect_tx(full, stage_tx);
+          tma_load_1d(dst, p.geom + goff * NGEO, NGEO * C::PLANE_BYTES, full);
 #pragma unroll
-            for (int a = NGEO; a < NF; a++) {
-              const double* src = p.pf[a - NGEO];
-              if (src) tma_load_1d(dst + a * C::PLANE_BYTES, src + goff, C::PLANE_BYTES, full);
-            }
-          }
-          if (kk[s] == 1 && it[s] + 1 < nmy[s]) {   // L2 prefetch of the slot's next base-flow element
-            int en = (int)blockIdx.x * NE + s + (it[s] + 1) * nslots;
-            if (p.elem_list) en = __ldg(p.elem_list + en);
-            if (elect_one()) {
-#pragma unroll
-              for (int c = 0; c < 3; c++) l2_prefetch_bulk(p.ub[c] + (size_t)en * N, N * 8);
-            }
-          }
-        } else {
-          {
-            double* d = reinterpret_cast<double*>(dst);
-            const double* src = p.geom + goff * NGEO;
-            for (int x = lane; x < NGEO * PLANE; x += 32) cp_async_8(d + x, src + x);
-          }
-#pragma unroll 1
           for (int a = NGEO; a < NF; a++) {
             const double* src = p.pf[a - NGEO];
-            if (!src) continue;
-            double* d = reinterpret_cast<double*>(dst + a * C::PLANE_BYTES);
-            for (int x = lane; x < PLANE; x += 32) cp_async_8(d + x, src + goff + x);
+            if (src) tma_load_1d(dst + NGEO * C::PLANE_BYTES + (a - NGEO) * C::FS, src + uoff, C::FS, full);
           }
-          cp_async_mbar_arrive(full);
+        }
+        if (kk[s] == 1 && it[s] + 1 < nmy[s]) {   // L2 prefetch of the slot's next base-flow element
+          int en = (int)blockIdx.x * NE + s + (it[s] + 1) * nslots;
+          if (p.elem_list) en = __ldg(p.elem_list + en);
+          en += p.elem_base;
+          const size_t eo = (size_t)en * N;
+          if (elect_one()) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+              l2_prefetch_bulk(p.ub[c] + (C::ODD ? (eo & ~(size_t)1) : eo), (N * 8) & ~15);
+          }
         }
         if (++st[s] == NS) { st[s] = 0; ph[s] ^= 1; }
         if (++kk[s] == LX) {
@@ -215,7 +214,6 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
       }
       if (!progressed) __nanosleep(32);
     }
-    if constexpr (!C::BULK) asm volatile("cp.async.wait_all;" ::: "memory");
     return;
   }
 
@@ -240,6 +238,7 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
   for (int it = 0; it < n_my; it++) {
     int e = g0 + it * nslots;
     if (p.elem_list) e = p.elem_list[e];
+    e += p.elem_base;
     const size_t ebase = (size_t)e * N;
 
     // ---- phase A: r- and s-derivatives of the base flow as whole-pencil tasks, t-pencils to registers
@@ -293,26 +292,29 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
     for (int k = 0; k < LX; k++) {
       mbar_wait(&sbar[st * 2], (uint32_t)ph);
       const double* stage = reinterpret_cast<const double*>(ring + st * C::STAGE_BYTES);
+      // user fields follow the geometry block, FS bytes apart, shifted by one double for odd (e + k)
+      const double* ustage = stage + NGEO * PLANE + (C::ODD ? (int)((ebase + (size_t)k * PLANE) & 1) : 0);
+      constexpr int UF = C::FS / 8;
       const int pl = tj * LX + ti;
       const int q = (k * LX + tj) * LX + ti;
       const int qs = wsw<LX>(q);
       // all ring reads of this plane first, then the stage goes back to the producer
-      const double v0 = stage[(R_V + 0) * PLANE + pl], v1 = stage[(R_V + 1) * PLANE + pl],
-                   v2 = stage[(R_V + 2) * PLANE + pl];
+      const double v0 = ustage[(R_V - NGEO + 0) * UF + pl], v1 = ustage[(R_V - NGEO + 1) * UF + pl],
+                   v2 = ustage[(R_V - NGEO + 2) * UF + pl];
       double G[9];
 #pragma unroll
       for (int a = 0; a < 9; a++) G[a] = stage[(R_G + a) * PLANE + pl];
       double Bm = 0.0, chi = 0.0, fs0 = 0.0, fs1 = 0.0, fs2 = 0.0, fi0 = 0.0, fi1 = 0.0, fi2 = 0.0;
       if (flags & (FLAG_SOURCES | FLAG_FSTATIC)) Bm = stage[R_B * PLANE + pl];
-      if (flags & FLAG_SOURCES) chi = stage[R_RHO * PLANE + pl];
+      if (flags & FLAG_SOURCES) chi = ustage[(R_RHO - NGEO) * UF + pl];
       if constexpr (NF > NF_FUSED) {
         if (flags & FLAG_FSTATIC) {
-          fs0 = stage[(R_FS + 0) * PLANE + pl]; fs1 = stage[(R_FS + 1) * PLANE + pl];
-          fs2 = stage[(R_FS + 2) * PLANE + pl];
+          fs0 = ustage[(R_FS - NGEO + 0) * UF + pl]; fs1 = ustage[(R_FS - NGEO + 1) * UF + pl];
+          fs2 = ustage[(R_FS - NGEO + 2) * UF + pl];
         }
         if (flags & FLAG_ACCUM) {
-          fi0 = stage[(R_FIN + 0) * PLANE + pl]; fi1 = stage[(R_FIN + 1) * PLANE + pl];
-          fi2 = stage[(R_FIN + 2) * PLANE + pl];
+          fi0 = ustage[(R_FIN - NGEO + 0) * UF + pl]; fi1 = ustage[(R_FIN - NGEO + 1) * UF + pl];
+          fi2 = ustage[(R_FIN - NGEO + 2) * UF + pl];
         }
       }
       __syncwarp();

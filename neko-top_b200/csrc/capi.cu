@@ -246,7 +246,7 @@ int launch_v2_cfg(Handle* h, const LaunchArgs& a) {
   memset(&p, 0, sizeof p);
   for (int i = 0; i < LX * LX; i++) p.D[i] = h->D[i];
   for (int i = 0; i < LX; i++) p.w[i] = h->w[i];
-  const size_t eoff = (size_t)a.elem_begin * C::N;
+  const size_t eoff = 0;             // the element offset goes in as an index (alignment for odd lx)
   for (int c = 0; c < 3; c++) p.ub[c] = a.vb[c] + eoff;
   unsigned flags = 0;
   if (!h->geom_pack) return fail(B200_ERR_STATE, "packed geometry image missing (set_geometry)");
@@ -281,6 +281,7 @@ int launch_v2_cfg(Handle* h, const LaunchArgs& a) {
   p.chi_out = a.chi_out ? a.chi_out + eoff : nullptr;
   p.elem_list = a.elem_list;
   p.nelem = a.nelem;
+  p.elem_base = a.elem_begin;
   p.flags = flags;
   p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
   p.K_sens = h->if_lube ? h->K_sens : 0.0;
@@ -479,9 +480,12 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
   if (cfg >= 100) return launch_fused_v1(h, a);
   switch (h->lx) {
     case 4: return launch_v2<4, 8, 4, 224>(h, a);
-    case 5: return launch_v2<5, 8, 2, 224>(h, a);
-    case 6: return launch_v2<6, 4, 2, 224>(h, a);
-    case 7: return launch_v2<7, 4, 2, 224>(h, a);
+    // lx != 8 (v2): configurations from the r01j sweep (tools/lxsweep.py, profiles/r01j_lxsweep.jsonl).  What
+    // matters most is a warp count whose per-scheduler register share avoids spills (the register file is
+    // split over four schedulers: 9-12 warps -> 168 registers, <= 8 warps -> 255); cfg 32 = the older choice.
+    case 5: return cfg == 32 ? launch_v2<5, 8, 2, 224>(h, a) : launch_v2<5, 11, 2, 168>(h, a);
+    case 6: return cfg == 32 ? launch_v2<6, 4, 2, 224>(h, a) : launch_v2<6, 5, 2, 168>(h, a);
+    case 7: return cfg == 32 ? launch_v2<7, 4, 2, 224>(h, a) : launch_v2<7, 3, 4, 255, 3, 2>(h, a);
     case 8:
       switch (cfg) {
         case 1: return launch_v2<8, 4, 2, 224>(h, a);
@@ -500,7 +504,7 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
         case 25: return launch_v3<3, 4, 1, 168>(h, a);       // 12 warps, 138 KB
         default: return launch_v3_default(h, a);
       }
-    case 9: return launch_v2<9, 3, 2, 200>(h, a);
+    case 9: return cfg == 32 ? launch_v2<9, 3, 2, 200>(h, a) : launch_v2<9, 2, 4, 255, 2, 2>(h, a);
     case 10: return launch_v2<10, 2, 2, 224>(h, a);
     default: return fail(B200_ERR_ARG, "lx=%d not instantiated (4..10)", h->lx);
   }

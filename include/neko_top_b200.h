@@ -9,7 +9,10 @@
  *   - masks are 1-based linear indices                 (math_ext_kernel.h:49 `a[mask[i]-1]`)
  * exactly as /root/reference/sources/neko_ext/math/bcknd/device_math_ext.f90:43-103 binds
  * /root/reference/sources/neko_ext/math/bcknd/device/cuda/math_ext.cu:49-108.
- * Fields are fp64 (Neko `rp` = `dp`), Fortran column-major x(lx,lx,lx,nelv).
+ * Fields are fp64 (Neko `rp` = `dp`), Fortran column-major x(lx,lx,lx,nelv); device field pointers must be
+ * 16-byte aligned (any cudaMalloc / Neko device_alloc pointer is).  For odd lx the element kernels fetch
+ * k-planes with 16-byte aligned TMA windows and may READ (never write) up to 8 bytes past the last double
+ * of an input field, inside the same 16-byte granule -- always inside the allocation.
  *
  * Error convention (reference: neko_error / CUDA_CHECK abort the job, math_ext.cu:56): every call
  * returns 0 on success; on failure it prints the reason to stderr and, unless

@@ -65,7 +65,8 @@ struct AdvCfg {
   static constexpr bool INTERP = (LXD != LX);
   static constexpr int NTHR = ((PL + 31) / 32) * 32;
   static constexpr int S1 = LXD * LX * LX, S2 = LXD * LXD * LX;
-  static constexpr int X_INTERP = INTERP ? (N + S1 + S2) : 0;
+  static constexpr int NB = 3;                                   // fields interpolated per batch
+  static constexpr int X_INTERP = INTERP ? NB * S1 : 0;
   static constexpr int X_PLANES = (MODE == ADV_ADJOINT) ? 2 * 6 * PL : 0;
   static constexpr int X_SIZE = X_INTERP > X_PLANES ? X_INTERP : X_PLANES;
   static constexpr int X_OFF = 6 * ND;
@@ -116,6 +117,71 @@ __device__ __forceinline__ void interp_to_fine(const double* __restrict__ src, d
   // the caller's next barrier (or the next call's first one) orders s2 reads before it is rewritten
 }
 
+template <int V>
+struct IntC { static constexpr int value = V; };
+
+// (J x J x J) of NB fields of one element at once: src[f] (LX^3, global) -> T + f*ND (LXD^3, shared).  Every
+// stage is a set of independent pencil tasks -- a thread pulls the LX (or LXD) values of a pencil into
+// registers and produces all outputs of that pencil with J as constant-bank operands, so the only shared
+// traffic is the data itself, and one barrier separates the stages for all NB fields together:
+//   1. rows (m,n):      s1(a,m,n) = sum_l J(a,l) u(l,m,n)           global -> X (NB * LXD*LX*LX doubles)
+//   2. pencils (a,n):   s2(a,b,n) = sum_m s1(a,m,n) J(b,m)          X -> first LX planes of T_f
+//   3. columns (a,b):   T(a,b,c)  = sum_n s2(a,b,n) J(c,n)          in place (a column is thread-private)
+template <int LX, int LXD, int NTHR, int NB>
+__device__ __forceinline__ void interp_batch(const double* const (&src)[NB], double* T, double* X,
+                                             const double* Jc, int tid) {
+  constexpr int ND = LXD * LXD * LXD, PL = LXD * LXD, S1 = LXD * LX * LX;
+  for (int t = tid; t < NB * LX * LX; t += NTHR) {
+    const int f = t / (LX * LX), mn = t - f * (LX * LX);
+    const double* sp = src[0];               // (no run-time indexing of the pointer array: it would go to local memory)
+#pragma unroll
+    for (int q = 1; q < NB; q++) sp = (f == q) ? src[q] : sp;
+    double u[LX];
+#pragma unroll
+    for (int l = 0; l < LX; l++) u[l] = __ldg(sp + l + LX * mn);
+    double* o = X + f * S1 + LXD * mn;
+#pragma unroll
+    for (int a = 0; a < LXD; a++) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < LX; l++) s = fma(Jc[a + LXD * l], u[l], s);
+      o[a] = s;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < NB * LXD * LX; t += NTHR) {
+    const int a = t % LXD, n = (t / LXD) % LX, f = t / (LXD * LX);
+    const double* in = X + f * S1 + a + LXD * LX * n;
+    double v[LX];
+#pragma unroll
+    for (int m = 0; m < LX; m++) v[m] = in[LXD * m];
+    double* o = T + f * ND + a + PL * n;
+#pragma unroll
+    for (int b = 0; b < LXD; b++) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < LX; m++) s = fma(v[m], Jc[b + LXD * m], s);
+      o[LXD * b] = s;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < NB * PL; t += NTHR) {
+    const int f = t / PL, ab = t - f * PL;
+    double* col = T + f * ND + ab;
+    double r[LX];
+#pragma unroll
+    for (int n = 0; n < LX; n++) r[n] = col[PL * n];
+#pragma unroll
+    for (int c = 0; c < LXD; c++) {
+      double s = 0.0;
+#pragma unroll
+      for (int n = 0; n < LX; n++) s = fma(r[n], Jc[c + LXD * n], s);
+      col[PL * c] = s;
+    }
+  }
+  __syncthreads();
+}
+
 template <int LX, int LXD, int MODE, int MAXREG>
 __global__ void __launch_bounds__(AdvCfg<LX, LXD, MODE>::NTHR) __maxnreg__(MAXREG)
 advop_kernel(const __grid_constant__ AdvParams<LX, LXD> p) {
@@ -142,16 +208,23 @@ advop_kernel(const __grid_constant__ AdvParams<LX, LXD> p) {
     const size_t eb = (size_t)e * N, ebd = (size_t)e * ND;
 
     // ---- phase 0: the six fields on the fine grid ----------------------------------------------------
+    if constexpr (C::INTERP) {
+      {
+        const double* const sv[3] = {p.v[0] + eb, p.v[1] + eb, p.v[2] + eb};
+        interp_batch<LX, LXD, NTHR, 3>(sv, T, X, p.J, tid);
+      }
+      {
+        const double* const sb[3] = {p.vb[0] + eb, p.vb[1] + eb, p.vb[2] + eb};
+        interp_batch<LX, LXD, NTHR, 3>(sb, T + 3 * ND, X, p.J, tid);
+      }
+    } else {
 #pragma unroll 1
-    for (int qf = 0; qf < 6; qf++) {
-      const double* src = (qf < 3 ? p.v[qf] : p.vb[qf - 3]) + eb;
-      if constexpr (C::INTERP) {
-        interp_to_fine<LX, LXD, NTHR>(src, T + qf * ND, X, Js, p.J, tid);
-      } else {
+      for (int qf = 0; qf < 6; qf++) {
+        const double* src = (qf < 3 ? p.v[qf] : p.vb[qf - 3]) + eb;
         for (int idx = tid; idx < N; idx += NTHR) T[qf * ND + idx] = __ldg(src + idx);
       }
+      __syncthreads();
     }
-    __syncthreads();
 
     // ---- phase 1: the k-column of thread (i,j) ----------------------------------------------------------
     double acc[3][LXD];
@@ -177,16 +250,17 @@ advop_kernel(const __grid_constant__ AdvParams<LX, LXD> p) {
         constexpr int NDF = (MODE == ADV_LINEAR) ? 6 : 3;
         double dr[NDF], ds[NDF], dt[NDF];
 #pragma unroll
-        for (int qd = 0; qd < NDF; qd++) {
-          const double* U = T + ((qd < 3) ? (3 + qd) : (qd - 3)) * ND;
-          double r = 0.0, s = 0.0, t = 0.0;
+        for (int qd = 0; qd < NDF; qd++) { dr[qd] = 0.0; ds[qd] = 0.0; dt[qd] = 0.0; }
 #pragma unroll
-          for (int m = 0; m < LXD; m++) {
-            r = fma(Ds[i + LXD * m], U[m + LXD * j + PL * k], r);
-            s = fma(Ds[j + LXD * m], U[i + LXD * m + PL * k], s);
-            t = fma(p.D[k + LXD * m], U[tid + PL * m], t);
+        for (int m = 0; m < LXD; m++) {
+          const double di = Ds[i + LXD * m], dj = Ds[j + LXD * m];   // one load of D(i,m), D(j,m) for all fields
+#pragma unroll
+          for (int qd = 0; qd < NDF; qd++) {
+            const double* U = T + ((qd < 3) ? (3 + qd) : (qd - 3)) * ND;
+            dr[qd] = fma(di, U[m + LXD * j + PL * k], dr[qd]);
+            ds[qd] = fma(dj, U[i + LXD * m + PL * k], ds[qd]);
+            dt[qd] = fma(p.D[k + LXD * m], U[tid + PL * m], dt[qd]);
           }
-          dr[qd] = r; ds[qd] = s; dt[qd] = t;
         }
 
         if constexpr (MODE == ADV_ADJOINT) {
@@ -229,18 +303,18 @@ advop_kernel(const __grid_constant__ AdvParams<LX, LXD> p) {
       if constexpr (MODE == ADV_ADJOINT) {
         __syncthreads();
         if (act) {
+          double rr[3] = {0.0, 0.0, 0.0}, ss[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-          for (int c = 0; c < 3; c++) {
-            const double* PR = PB + c * PL;
-            const double* PS = PB + (3 + c) * PL;
-            double r = 0.0, s = 0.0;
+          for (int m = 0; m < LXD; m++) {
+            const double di = Ds[m + LXD * i], dj = Ds[m + LXD * j];
 #pragma unroll
-            for (int m = 0; m < LXD; m++) {
-              r = fma(Ds[m + LXD * i], PR[m + LXD * j], r);
-              s = fma(Ds[m + LXD * j], PS[i + LXD * m], s);
+            for (int c = 0; c < 3; c++) {
+              rr[c] = fma(di, PB[c * PL + m + LXD * j], rr[c]);
+              ss[c] = fma(dj, PB[(3 + c) * PL + i + LXD * m], ss[c]);
             }
-            acc[c][k] += r + s;
           }
+#pragma unroll
+          for (int c = 0; c < 3; c++) acc[c][k] += rr[c] + ss[c];
         }
       }
     }
@@ -304,28 +378,48 @@ advop_kernel(const __grid_constant__ AdvParams<LX, LXD> p) {
           }
       }
       __syncthreads();
-      for (int idx = tid; idx < 3 * S1; idx += NTHR) {
-        const int c = idx / S1, r = idx - c * S1;
-        const int ii = r % LXD, m = (r / LXD) % LX, n = r / (LXD * LX);
-        const double* src = P1 + c * S2 + ii + PL * n;
-        double s = 0.0;
+      for (int t = tid; t < 3 * LXD * LX; t += NTHR) {     // pencils (c, i, n): contract j
+        const int ii = t % LXD, n = (t / LXD) % LX, c = t / (LXD * LX);
+        const double* in = P1 + c * S2 + ii + PL * n;
+        double v[LXD];
 #pragma unroll
-        for (int jj = 0; jj < LXD; jj++) s = fma(Js[jj + LXD * m], src[LXD * jj], s);
-        P2[idx] = s;
+        for (int jj = 0; jj < LXD; jj++) v[jj] = in[LXD * jj];
+        double* o = P2 + c * S1 + ii + LXD * LX * n;
+#pragma unroll
+        for (int m = 0; m < LX; m++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int jj = 0; jj < LXD; jj++) sacc = fma(p.J[jj + LXD * m], v[jj], sacc);
+          o[LXD * m] = sacc;
+        }
       }
       __syncthreads();
-      for (int pt = tid; pt < N; pt += NTHR) {
-        const int l = pt % LX, mn = pt / LX;
-        double o[3];
+      // rows (m,n), two tasks per row (first / second half of l): contract i, then the epilogue
+      constexpr int LH = (LX + 1) / 2;
+      auto row_task = [&](int mn, auto half_c) {
+        constexpr int HALF = decltype(half_c)::value;
+        constexpr int L0 = HALF * LH, L1 = HALF ? LX : LH;
+        double v[3][LXD];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const double* src = P2 + c * S1 + LXD * mn;
-          double s = 0.0;
+        for (int c = 0; c < 3; c++)
 #pragma unroll
-          for (int ii = 0; ii < LXD; ii++) s = fma(Js[ii + LXD * l], src[ii], s);
-          o[c] = s;
+          for (int ii = 0; ii < LXD; ii++) v[c][ii] = P2[c * S1 + ii + LXD * mn];
+#pragma unroll
+        for (int l = L0; l < L1; l++) {
+          double o[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int ii = 0; ii < LXD; ii++) sacc = fma(p.J[ii + LXD * l], v[c][ii], sacc);
+            o[c] = sacc;
+          }
+          epilogue(l + LX * mn, o[0], o[1], o[2]);
         }
-        epilogue(pt, o[0], o[1], o[2]);
+      };
+      for (int t = tid; t < 2 * LX * LX; t += NTHR) {
+        if (t & 1) row_task(t >> 1, IntC<1>{});
+        else row_task(t >> 1, IntC<0>{});
       }
       __syncthreads();                         // T is rewritten by the next element
     } else {

@@ -1860,7 +1860,7 @@ int b200_adjrhs_step_host(void* handle, const double* vx, const double* vy, cons
   const double* in[7] = {vx, vy, vz, vxb, vyb, vzb, rho};
   double** st = h->stage;   // 0..6 inputs, 7..9 f, 10 sens
   // element chunks: copy chunk c+1 while chunk c computes; sens goes back as soon as its chunk is done
-  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(16, h->nelv / 256));
+  const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(32, h->nelv / 256));
   while ((int)h->ev_h2d.size() < nchunk) {
     cudaEvent_t a, b;
     CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));

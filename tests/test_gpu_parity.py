@@ -429,3 +429,36 @@ def test_reference_pipe_mesh(oracle, lx, dealias):
         assert rel_l2(c(f[k]), oracle.gs_add(fo[k], cid, nc)) <= TOL
     assert rel_l2(c(sens), so) <= TOL
     op.free()
+
+
+def test_edge_cases(oracle):
+    """Ragged inputs: a single element (no node classes at all), element counts that do not fill the persistent
+    grid's slots (1, 2, 5, 443, 445 elements at lx = 8 with 444 slots), and a mesh whose classes are all
+    singletons (empty gather-scatter)."""
+    ops = _ops()
+    lx = 8
+    sp_ops = lambda P: ops.fused_adjoint_rhs_t(ops.coef_t(ops.space_t(P.lx, P.D, P.w), P.nelv, P.cuda("G"), P.cuda("B")))
+    for ne in ((1, 1, 1), (2, 1, 1), (5, 1, 1), (443, 1, 1), (5, 89, 1)):
+        P = Problem(lx, ne=ne, deform=0.0 if ne[0] > 100 else 0.02)
+        fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+        cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
+        op = sp_ops(P)
+        op.gs.init(P.keys.reshape(-1).cuda())
+        for mode in (0, 2):
+            op.set_gs_mode(mode)
+            f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+            op.step(P.cuda("v"), P.cuda("ub"), f, rho=P.cuda("rho"), sens=sens)
+            for c in range(3):
+                assert rel_l2(f[c].cpu().numpy(), oracle.gs_add(fo[c], cid, nc)) <= TOL, (ne, mode)
+            assert rel_l2(sens.cpu().numpy(), so) <= TOL
+        op.free()
+    # all classes singletons: unique keys -> gs is the identity
+    P = Problem(lx, ne=(3, 2, 1), deform=0.02)
+    op = sp_ops(P)
+    op.gs.init(torch.arange(P.n, device="cuda", dtype=torch.int64))
+    fo, _, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    f = [_nan(P.n) for _ in range(3)]
+    op.step(P.cuda("v"), P.cuda("ub"), f, rho=P.cuda("rho"))
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), fo[c]) <= TOL
+    op.free()

@@ -175,6 +175,33 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 side
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and therefore its pinned staging buffers, first-touch) to the CPUs NVML
+    reports as local to the GPU -- what `numactl` / the MPI launcher does for a Neko rank.  Matters only for
+    the host-buffer (`e2e`) path; returns the number of CPUs bound to (0: left alone)."""
+    if os.environ.get("B200_BENCH_NO_AFFINITY"):
+        return 0
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local).uuid))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -191,6 +218,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: neko_top_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if N > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -338,7 +366,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(ne, lx, N), "lx": lx, "elements_per_gpu": ne ** 3,
-                       "dof_per_gpu": n, "rank_grid": list(workloads.rank_grid(N)),
+                       "dof_per_gpu": n, "rank_grid": list(workloads.rank_grid(N)), "host_cpus_bound": numa,
                        "l2": "inputs (21 fields, %.1f GB per GPU) exceed the 126 MB L2; no flush needed"
                              % (21 * n * 8 / 1e9)},
             "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,

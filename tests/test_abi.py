@@ -76,3 +76,16 @@ def test_fortran_shim_binds_every_symbol():
     src = open(path).read().lower()
     for n in _declared():
         assert f"name='{n}'" in src or f'name="{n}"' in src, f"{n} missing from the Fortran interface block"
+
+
+def test_c99_consumer_links_and_runs(L):
+    """csrc/host/abi_check.c (C99, -pedantic -Werror) includes the header, takes the address of every declared
+    entry point, links against the shared library and exercises the no-abort error path; the C++17 mirror
+    header csrc/host/neko_top_plugin.hpp must compile against the same header.  No GPU needed."""
+    import subprocess
+    host = os.path.join(ROOT, "neko-top_b200", "csrc", "host")
+    subprocess.check_call(["make", "-B", "-C", host], stdout=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(host, "abi_check")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    from neko_top_b200 import _lib
+    assert f"{len(_lib.SYMBOLS)} entry points" in out.stdout

@@ -191,6 +191,20 @@ int b200_min_dissipation_objective(void* handle, const void* u, const void* v, c
 int b200_mask_exterior_const(void* fld, void* work, const void* mask_d, const int* mask_size, const double* c,
                              const int* n, void* stream);
 
+/* ---- PDE (Helmholtz) filter ------------------------------------------------------------
+ * PDE_filter_t%apply / %apply_backward (mapping_functions/PDE_filter_mapping.f90:212-363): solve
+ *   (r^2 K + M) x = gs(B * x_in)        (coef%h1 = r^2, coef%h2 = 1, ifh2; no Dirichlet conditions)
+ * with Neko's preconditioned conjugate gradients (ax_helm, gs_op on every operator application, inner products
+ * weighted with coef%mult, zero initial guess, stop when sqrt(r.mult.r)*norm_fac < abs_tol).  Both directions of
+ * the filter are this call (the backward pass filters the sensitivity with the same operator).
+ * jacinv = coef%jacinv_d, mult = coef%mult_d; *precond: 0 = ident, otherwise jacobi (diagonal without the
+ * cross terms of deformed elements); norm_fac = 1/sqrt(volume) as in Neko, NULL = 1.  In a multi-GPU run the
+ * inner products are summed over the ranks with ncclAllReduce.  Needs b200_gs_init. */
+int b200_pde_filter_apply(void* handle, void* x_out, const void* x_in, const void* jacinv, const void* mult,
+                          const double* radius, const double* abs_tol, const int* max_iter,
+                          const int* precond, const double* norm_fac, int* iters, double* res_start,
+                          double* res_final);
+
 /* ---- explicit time scheme around the RHS (adjoint/adjoint_pnpn.f90:665-666,688-696) --
  * Neko's rhs_maker types, argument order of the reference's call sites; all fields are device pointers of
  * *n doubles; coefficient arrays are HOST pointers.

@@ -20,7 +20,7 @@ SYMBOLS = [
     "b200_brinkman_compute",
     "b200_lube_compute", "b200_opcolv", "b200_ramp_forward", "b200_ramp_backward",
     "b200_sensitivity", "b200_steady_field_update",
-    "b200_curl", "b200_curlcurl_forcing", "b200_min_dissipation_objective", "b200_mask_exterior_const",
+    "b200_curl", "b200_curlcurl_forcing", "b200_min_dissipation_objective", "b200_mask_exterior_const", "b200_pde_filter_apply",
     "b200_sumab", "b200_makeabf", "b200_makebdf", "b200_makeabf_bdf",
     "b200_gs_init", "b200_gs_get_classes", "b200_gs_op", "b200_gs_op3",
     "b200_comm_unique_id", "b200_comm_init", "b200_gs_init_shared",

@@ -6,6 +6,7 @@
 
 #include "advop_kernel.cuh"
 #include "deriv_kernels.cuh"
+#include "helm_kernels.cuh"
 
 namespace b200 {
 namespace {
@@ -104,7 +105,37 @@ cudaError_t deriv_lx(const DerivLaunch& a) {
   return cudaGetLastError();
 }
 
+template <int LX>
+cudaError_t helm_lx(const HelmLaunch& a) {
+  HelmParams<LX> p;
+  for (int i = 0; i < LX * LX; i++) p.D[i] = a.D[i];
+  for (int i = 0; i < LX; i++) p.w[i] = a.w[i];
+  p.u = a.u;
+  for (int g = 0; g < 9; g++) p.G[g] = a.G[g];
+  p.jacinv = a.jacinv; p.B = a.B; p.out = a.out; p.h1 = a.h1; p.h2 = a.h2; p.nelv = a.nelv;
+  constexpr int NTHR = ((LX * LX + 31) / 32) * 32;
+  const int grid = std::min(a.nelv, a.num_sm * 6);
+  if (grid < 1) return cudaSuccess;
+  if (a.mode == 0) helm_kernel<LX, 0><<<grid, NTHR, 0, a.stream>>>(p);
+  else helm_kernel<LX, 1><<<grid, NTHR, 0, a.stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+cudaError_t helm_launch(const HelmLaunch& a, const char** msg) {
+  *msg = nullptr;
+  switch (a.lx) {
+    case 4: return helm_lx<4>(a);
+    case 5: return helm_lx<5>(a);
+    case 6: return helm_lx<6>(a);
+    case 7: return helm_lx<7>(a);
+    case 8: return helm_lx<8>(a);
+    case 9: return helm_lx<9>(a);
+    case 10: return helm_lx<10>(a);
+    default: *msg = "lx not instantiated (4..10)"; return cudaErrorInvalidValue;
+  }
+}
 
 cudaError_t deriv_launch(const DerivLaunch& a, const char** msg) {
   *msg = nullptr;

@@ -49,6 +49,22 @@ struct DerivLaunch {
 };
 cudaError_t deriv_launch(const DerivLaunch& a, const char** msg);
 
+// Helmholtz operator of the PDE filter (helm_kernels.cuh): mode 0 -> out = A u, mode 1 -> out = diag(A)
+struct HelmLaunch {
+  int lx, mode, nelv;
+  const double* D;            // HOST
+  const double* w;            // HOST
+  const double* u;
+  const double* G[9];
+  const double* jacinv;
+  const double* B;
+  double* out;
+  double h1, h2;
+  int num_sm;
+  cudaStream_t stream;
+};
+cudaError_t helm_launch(const HelmLaunch& a, const char** msg);
+
 // default fine-grid order of advection_adjoint_factory (adjoint/advection_adjoint_fctry.f90:70,89): 3*lx/2
 inline int advop_default_lxd(int lx) { return 3 * lx / 2; }
 

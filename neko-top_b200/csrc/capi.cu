@@ -7,6 +7,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -25,6 +26,7 @@
 #include "gs_kernels.cuh"
 #include "pointwise_kernels.cuh"
 #include "deriv_kernels.cuh"
+#include "helm_kernels.cuh"
 
 namespace {
 
@@ -1466,6 +1468,111 @@ int b200_mask_exterior_const(void* fld, void* work, const void* mask_d, const in
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(fld, work, sizeof(double) * (size_t)*n, cudaMemcpyDeviceToDevice, st));
+  return B200_OK;
+}
+
+// ---- PDE (Helmholtz) filter: SURVEY.md 8f row 4 ------------------------------------------------------------
+static int helm_run(Handle* h, int mode, const double* u, const double* jacinv, double* out, double h1, double h2) {
+  HelmLaunch L;
+  memset(&L, 0, sizeof L);
+  L.lx = h->lx; L.mode = mode; L.nelv = h->nelv; L.D = h->D; L.w = h->w; L.u = u;
+  for (int g = 0; g < 9; g++) L.G[g] = h->G[g];
+  L.jacinv = jacinv; L.B = h->B; L.out = out; L.h1 = h1; L.h2 = h2;
+  L.num_sm = h->num_sm; L.stream = h->stream;
+  const char* msg = nullptr;
+  cudaError_t e = helm_launch(L, &msg);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "Helmholtz kernel: %s", msg ? msg : cudaGetErrorString(e));
+  if (h->nelv > 0) LAUNCHED();
+  return B200_OK;
+}
+
+// glsc3(a, mult, b): deterministic local sum, then the sum over ranks (Neko: MPI_Allreduce; here NCCL)
+static int glsc3_global(Handle* h, const double* a, const double* m, const double* b, double* result) {
+  const int nblk = 1024;
+  if (!h->d_partial) if (int r = dmalloc(&h->d_partial, (size_t)nblk)) return r;
+  dot3_partial_kernel<<<nblk, 256, 0, h->stream>>>(a, m, b, h->n, h->d_partial);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  std::vector<double> part(nblk);
+  CK(cudaMemcpyAsync(part.data(), h->d_partial, sizeof(double) * nblk, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double s = 0.0;
+  for (double v : part) s += v;
+  if (h->comm && h->nranks > 1) {
+    CK(cudaMemcpyAsync(h->d_partial, &s, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    NK(ncclAllReduce(h->d_partial, h->d_partial, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&s, h->d_partial, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  *result = s;
+  return B200_OK;
+}
+
+int b200_pde_filter_apply(void* handle, void* x_out, const void* x_in, const void* jacinv, const void* mult,
+                          const double* radius, const double* abs_tol, const int* max_iter,
+                          const int* precond, const double* norm_fac, int* iters, double* res_start,
+                          double* res_final) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  if (!x_out || !x_in || !jacinv || !mult || !radius || !abs_tol || !max_iter)
+    return fail(B200_ERR_ARG, "pde_filter_apply: null argument");
+  if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
+  if (!h->have_gs) return fail(B200_ERR_STATE, "pde_filter_apply: b200_gs_init not called");
+  CK(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  if (!h->work6 && n > 0) if (int r = dmalloc(&h->work6, 6 * (size_t)n)) return r;
+  double *rr = h->work6, *pp = rr + n, *zz = pp + n, *ww = zz + n, *dinv = ww + n;
+  double* x = (double*)x_out;
+  const double* mlt = (const double*)mult;
+  const double h1 = (*radius) * (*radius), h2 = 1.0;          // PDE_filter_mapping.f90:229-231 / :240-244
+  const double nf = norm_fac ? *norm_fac : 1.0;
+  const bool jacobi = !precond || *precond != 0;
+  const int threads = 256;
+  const int grid = grid_for(n, threads, h->num_sm, 8);
+  cudaStream_t st = h->stream;
+  // RHS = B * X_in, direct-stiffness summed (:231,251)
+  cg_col3_kernel<<<grid, threads, 0, st>>>(rr, (const double*)x_in, h->B, n);
+  LAUNCHED();
+  if (int r = b200_gs_op(handle, rr)) return r;
+  // Neko's Krylov solvers start from x = 0 (the field_copy at :248 is overwritten by the solver)
+  CK(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
+  CK(cudaMemsetAsync(pp, 0, sizeof(double) * (size_t)n, st));
+  if (jacobi) {
+    if (int r = helm_run(h, 1, nullptr, (const double*)jacinv, dinv, h1, h2)) return r;
+    if (int r = b200_gs_op(handle, dinv)) return r;
+    cg_invert_kernel<<<grid, threads, 0, st>>>(dinv, n);
+    LAUNCHED();
+  }
+  double rtz1 = 1.0, rtz2, rtr = 0.0;
+  if (int r = glsc3_global(h, rr, mlt, rr, &rtr)) return r;
+  double rnorm = sqrt(rtr) * nf;
+  if (res_start) *res_start = rnorm;
+  int it = 0;
+  for (it = 1; it <= *max_iter && rnorm >= *abs_tol; it++) {
+    const double* z = rr;
+    if (jacobi) {
+      cg_col3_kernel<<<grid, threads, 0, st>>>(zz, rr, dinv, n);
+      LAUNCHED();
+      z = zz;
+    }
+    rtz2 = rtz1;
+    if (int r = glsc3_global(h, rr, mlt, z, &rtz1)) return r;
+    const double beta = (it == 1) ? 0.0 : rtz1 / rtz2;
+    cg_p_update_kernel<<<grid, threads, 0, st>>>(pp, z, beta, n);
+    LAUNCHED();
+    if (int r = helm_run(h, 0, pp, (const double*)jacinv, ww, h1, h2)) return r;
+    if (int r = b200_gs_op(handle, ww)) return r;
+    double pap = 0.0;
+    if (int r = glsc3_global(h, ww, mlt, pp, &pap)) return r;
+    const double alpha = rtz1 / pap;
+    cg_xr_update_kernel<<<grid, threads, 0, st>>>(x, rr, pp, ww, alpha, n);
+    LAUNCHED();
+    if (int r = glsc3_global(h, rr, mlt, rr, &rtr)) return r;
+    rnorm = sqrt(rtr) * nf;
+  }
+  CK(cudaGetLastError());
+  if (iters) *iters = it - 1;
+  if (res_final) *res_final = rnorm;
   return B200_OK;
 }
 

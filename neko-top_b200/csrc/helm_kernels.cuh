@@ -1,0 +1,151 @@
+// Helmholtz operator and the pieces of the conjugate-gradient solve behind the PDE filter
+// (/root/reference/sources/mapping_functions/PDE_filter_mapping.f90:212-363), fp64.
+// Neko's ax_helm / jacobi / cg are not vendored; restated from their published CPU back-ends:
+//   ax_helm:  w = D_r^T(h1 (G11 ur + G12 us + G13 ut)) + D_s^T(h1 (G12 ur + G22 us + G23 ut))
+//               + D_t^T(h1 (G13 ur + G23 us + G33 ut)) + h2 B u,          (ur, us, ut) = (D_r, D_s, D_t) u
+//   coef_t:   G11 = (drdx^2 + drdy^2 + drdz^2) jacinv w3, ..., G12 = (drdx dsdx + drdy dsdy + drdz dsdz) jacinv w3, ...
+// The six G_ij are formed on the fly from the nine cofactors the handle already holds (the filter runs once
+// per optimisation iteration; it is a latency-bound solver, not the hot path).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+template <int LX>
+struct HelmParams {
+  double D[LX * LX];
+  double w[LX];
+  const double* u;
+  const double* G[9];
+  const double* jacinv;
+  const double* B;
+  double* out;          // w (ax) or the diagonal
+  double h1, h2;
+  int nelv;
+};
+
+// MODE 0: out = A u ; MODE 1: out = diag(A) (Neko jacobi without the cross terms of deformed elements)
+template <int LX, int MODE>
+__global__ void __launch_bounds__(((LX * LX + 31) / 32) * 32)
+helm_kernel(const __grid_constant__ HelmParams<LX> p) {
+  constexpr int N = LX * LX * LX, PL = LX * LX, NTHR = ((PL + 31) / 32) * 32;
+  __shared__ double U[N], WR[N], WS[N], WT[N];
+  __shared__ double Ds[PL];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < PL; idx += NTHR) Ds[idx] = p.D[idx];
+  const bool act = tid < PL;
+  const int i = act ? tid % LX : 0, j = act ? tid / LX : 0;
+  const double wij = p.w[i] * p.w[j];
+  for (int e = blockIdx.x; e < p.nelv; e += gridDim.x) {
+    const size_t eb = (size_t)e * N;
+    __syncthreads();
+    if constexpr (MODE == 0)
+      for (int idx = tid; idx < N; idx += NTHR) U[idx] = __ldg(p.u + eb + idx);
+    __syncthreads();
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < LX; k++) {
+        const int pidx = tid + PL * k;
+        double g[9];
+#pragma unroll
+        for (int a = 0; a < 9; a++) g[a] = __ldg(p.G[a] + eb + pidx);
+        const double sc = __ldg(p.jacinv + eb + pidx) * (wij * p.w[k]);
+        // g = drdx,dsdx,dtdx, drdy,dsdy,dtdy, drdz,dsdz,dtdz
+        const double G11 = (g[0] * g[0] + g[3] * g[3] + g[6] * g[6]) * sc;
+        const double G22 = (g[1] * g[1] + g[4] * g[4] + g[7] * g[7]) * sc;
+        const double G33 = (g[2] * g[2] + g[5] * g[5] + g[8] * g[8]) * sc;
+        if constexpr (MODE == 0) {
+          const double G12 = (g[0] * g[1] + g[3] * g[4] + g[6] * g[7]) * sc;
+          const double G13 = (g[0] * g[2] + g[3] * g[5] + g[6] * g[8]) * sc;
+          const double G23 = (g[1] * g[2] + g[4] * g[5] + g[7] * g[8]) * sc;
+          double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+          for (int m = 0; m < LX; m++) {
+            ur = fma(Ds[i + LX * m], U[m + LX * j + PL * k], ur);
+            us = fma(Ds[j + LX * m], U[i + LX * m + PL * k], us);
+            ut = fma(p.D[k + LX * m], U[tid + PL * m], ut);
+          }
+          WR[pidx] = p.h1 * (G11 * ur + G12 * us + G13 * ut);
+          WS[pidx] = p.h1 * (G12 * ur + G22 * us + G23 * ut);
+          WT[pidx] = p.h1 * (G13 * ur + G23 * us + G33 * ut);
+        } else {
+          WR[pidx] = G11; WS[pidx] = G22; WT[pidx] = G33;
+        }
+      }
+    }
+    __syncthreads();
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < LX; k++) {
+        const int pidx = tid + PL * k;
+        double s = 0.0;
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int m = 0; m < LX; m++) {
+            s = fma(Ds[m + LX * i], WR[m + LX * j + PL * k], s);
+            s = fma(Ds[m + LX * j], WS[i + LX * m + PL * k], s);
+            s = fma(p.D[m + LX * k], WT[tid + PL * m], s);
+          }
+          s += p.h2 * __ldg(p.B + eb + pidx) * U[pidx];
+        } else {
+#pragma unroll
+          for (int m = 0; m < LX; m++) {
+            const double a = Ds[m + LX * i], b = Ds[m + LX * j], c = p.D[m + LX * k];
+            s = fma(a * a, WR[m + LX * j + PL * k], s);
+            s = fma(b * b, WS[i + LX * m + PL * k], s);
+            s = fma(c * c, WT[tid + PL * m], s);
+          }
+          s = p.h1 * s + p.h2 * __ldg(p.B + eb + pidx);
+        }
+        p.out[eb + pidx] = s;
+      }
+    }
+  }
+}
+
+// deterministic partial sums of a_i * m_i * b_i (Neko glsc3 with the multiplicity weights, local part)
+static __global__ void __launch_bounds__(256) dot3_partial_kernel(const double* __restrict__ a,
+                                                                 const double* __restrict__ m,
+                                                                 const double* __restrict__ b, int64_t n,
+                                                                 double* __restrict__ partial) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = (lo + per < n) ? lo + per : n;
+  for (int64_t q = lo + threadIdx.x; q < hi; q += 256) s += a[q] * m[q] * b[q];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// small vector updates of the CG iteration
+static __global__ void cg_col3_kernel(double* __restrict__ out, const double* __restrict__ a,
+                                      const double* __restrict__ b, int64_t n) {   // out = a*b
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[i] * b[i];
+}
+static __global__ void cg_invert_kernel(double* __restrict__ a, int64_t n) {       // a = 1/a
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = 1.0 / a[i];
+}
+static __global__ void cg_p_update_kernel(double* __restrict__ p, const double* __restrict__ z, double beta,
+                                          int64_t n) {                              // p = beta*p + z (add2s1)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = beta * p[i] + z[i];
+}
+static __global__ void cg_xr_update_kernel(double* __restrict__ x, double* __restrict__ r,
+                                           const double* __restrict__ p, const double* __restrict__ w,
+                                           double alpha, int64_t n) {               // x += alpha p ; r -= alpha w
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    x[i] = x[i] + alpha * p[i];
+    r[i] = r[i] - alpha * w[i];
+  }
+}
+
+}  // namespace b200

@@ -210,6 +210,17 @@ module neko_top_b200
        type(c_ptr), value :: stream
      end function b200_mask_exterior_const
 
+     integer(c_int) function b200_pde_filter_apply(handle, x_out_d, x_in_d, &
+          jacinv_d, mult_d, radius, abs_tol, max_iter, precond, norm_fac, &
+          iters, res_start, res_final) bind(c, name='b200_pde_filter_apply')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: x_out_d, x_in_d, jacinv_d, mult_d
+       real(c_double) :: radius, abs_tol, norm_fac
+       integer(c_int) :: max_iter, precond, iters
+       real(c_double) :: res_start, res_final
+     end function b200_pde_filter_apply
+
      integer(c_int) function b200_sumab(ue_d, ve_d, we_d, u_d, v_d, w_d, &
           ulag1_d, vlag1_d, wlag1_d, ulag2_d, vlag2_d, wlag2_d, ab, nab, n, &
           stream) bind(c, name='b200_sumab')

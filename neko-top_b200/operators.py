@@ -292,6 +292,29 @@ def mask_exterior_const(fld, mask, const):
                                               _ci(fld.numel()), _stream_ptr()))
 
 
+class PDE_filter_t:
+    """mapping_functions/PDE_filter_mapping.f90:52-363: apply_forward / apply_backward = one Helmholtz solve."""
+
+    def __init__(self, handle, coef, mult, r, abs_tol=1e-10, max_iter=800, precond="jacobi", norm_fac=1.0):
+        self.handle, self.coef, self.mult = handle, coef, mult
+        self.r, self.abs_tol, self.max_iter, self.precond, self.norm_fac = r, abs_tol, max_iter, precond, norm_fac
+        self.ksp_results = None
+
+    def _solve(self, X_out, X_in):
+        it, r0, r1 = C.c_int(0), C.c_double(0), C.c_double(0)
+        check(_lib.lib().b200_pde_filter_apply(self.handle.handle.h, _ptr(X_out), _ptr(X_in), _ptr(self.coef.jacinv),
+                                               _ptr(self.mult), _cd(self.r), _cd(self.abs_tol), _ci(self.max_iter),
+                                               _ci(0 if self.precond == "ident" else 1), _cd(self.norm_fac),
+                                               C.byref(it), C.byref(r0), C.byref(r1)))
+        self.ksp_results = (it.value, r0.value, r1.value)
+
+    def apply_forward(self, X_out, X_in):
+        self._solve(X_out, X_in)
+
+    def apply_backward(self, dF_dX_in, dF_dX_out, X_in=None):
+        self._solve(dF_dX_in, dF_dX_out)
+
+
 # ---- explicit time scheme around the RHS (Neko rhs_maker types; adjoint_pnpn.f90:665-666,688-696) ---------
 def _dv(a):
     v = np.ascontiguousarray(a, dtype=np.float64)

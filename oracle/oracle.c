@@ -696,6 +696,41 @@ double orc_min_dissipation_objective(double out[2], const double *u, const doubl
   return (out[0] + (chi ? 0.5 * K * out[1] : 0.0)) * obj_scale;
 }
 
+/* ============================ Helmholtz operator (Neko ax_helm, restated) ================== */
+
+void orc_ax_helm(double *w, const double *u, int lx, int nelv, const double *D, const double *wq,
+                 double *const G[9], const double *jacinv, const double *B, double h1, double h2) {
+  size_t N = (size_t)lx * lx * lx;
+  double *w3 = (double *)malloc(sizeof(double) * N);
+  make_w3(w3, wq, lx);
+#pragma omp parallel
+  {
+    double *ur = (double *)malloc(sizeof(double) * 6 * N), *us = ur + N, *ut = us + N;
+    double *a = ut + N, *b = a + N, *c = b + N;
+#pragma omp for schedule(static)
+    for (int e = 0; e < nelv; e++) {
+      size_t o = N * e;
+      local_grad(ur, us, ut, u + o, D, lx);
+      for (size_t i = 0; i < N; i++) {
+        const double sc = jacinv[o + i] * w3[i];
+        const double rx = G[0][o + i], sx = G[1][o + i], tx = G[2][o + i];
+        const double ry = G[3][o + i], sy = G[4][o + i], ty = G[5][o + i];
+        const double rz = G[6][o + i], sz = G[7][o + i], tz = G[8][o + i];
+        const double G11 = (rx * rx + ry * ry + rz * rz) * sc, G22 = (sx * sx + sy * sy + sz * sz) * sc;
+        const double G33 = (tx * tx + ty * ty + tz * tz) * sc, G12 = (rx * sx + ry * sy + rz * sz) * sc;
+        const double G13 = (rx * tx + ry * ty + rz * tz) * sc, G23 = (sx * tx + sy * ty + sz * tz) * sc;
+        a[i] = h1 * (G11 * ur[i] + G12 * us[i] + G13 * ut[i]);
+        b[i] = h1 * (G12 * ur[i] + G22 * us[i] + G23 * ut[i]);
+        c[i] = h1 * (G13 * ur[i] + G23 * us[i] + G33 * ut[i]);
+      }
+      local_gradT(w + o, a, b, c, D, lx);
+      for (size_t i = 0; i < N; i++) w[o + i] += h2 * B[o + i] * u[o + i];
+    }
+    free(ur);
+  }
+  free(w3);
+}
+
 /* ============================ explicit time scheme (Neko rhs_maker, restated) ============== */
 
 void orc_sumab(double *ue, double *ve, double *we, const double *u, const double *v, const double *w,

@@ -131,6 +131,12 @@ double orc_min_dissipation_objective(double out[2], const double *u, const doubl
                                      double *const G[9], const double *jacinv, const double *B,
                                      const int *mask, int mask_size, double K, double obj_scale);
 
+/* ---- PDE filter: Neko ax_helm restated (not vendored) ---------------------------------
+ * w = D^T (h1 G D u) + h2 B u per element, G_ij = sum_k (dr_i/dx_k)(dr_j/dx_k) * jacinv * w3 from the cofactors.
+ * The filter itself, (r^2 K + M) x = gs(B x_in), is solved in tests/ by assembling this operator. */
+void orc_ax_helm(double *w, const double *u, int lx, int nelv, const double *D, const double *wq,
+                 double *const G[9], const double *jacinv, const double *B, double h1, double h2);
+
 /* ---- explicit time scheme around the RHS (adjoint_pnpn.f90:665-666,688-696) -------------------
  * The three rhs_maker types live in Neko (src/fluid/rhs_maker*.f90, not vendored); restated from
  * Neko's published CPU back-end (rhs_maker_cpu.f90), argument order of the reference's call sites.

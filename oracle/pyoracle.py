@@ -291,6 +291,28 @@ def mask_exterior_const(fld, mask, c):
     return fld
 
 
+def ax_helm(u, lx, nelv, D, w, G, jacinv, B, h1, h2):
+    out = np.zeros(lx ** 3 * nelv)
+    lib().orc_ax_helm(_p(out), _p(f64(u)), C.c_int(lx), C.c_int(nelv), _p(_colmajor(D)), _p(f64(w)), _G(G),
+                      _p(f64(jacinv)), _p(f64(B)), C.c_double(h1), C.c_double(h2))
+    return out
+
+
+def pde_filter_dense(x_in, lx, nelv, D, w, G, jacinv, B, cid, nclass, radius):
+    """Reference solution of the PDE filter on a SMALL mesh: assemble (r^2 K + M) on the unique nodes by applying
+    ax_helm + gs to unit vectors, solve with LAPACK.  Returns x on the local dofs."""
+    n = lx ** 3 * nelv
+    A = np.zeros((nclass, nclass))
+    for k in range(nclass):
+        e = (cid == k).astype(np.float64)
+        col = gs_add(ax_helm(e, lx, nelv, D, w, G, jacinv, B, radius * radius, 1.0), cid, nclass)
+        # one representative dof per class
+        A[:, k] = col[np.unique(cid, return_index=True)[1]]
+    rhs = gs_add(f64(x_in) * f64(B), cid, nclass)[np.unique(cid, return_index=True)[1]]
+    xg = np.linalg.solve(A, rhs)
+    return xg[cid]
+
+
 # ---- explicit time scheme (Neko rhs_maker) ----
 def sumab(u, ulag1, ulag2, ab, nab):
     out = [np.zeros_like(f64(u[0])) for _ in range(3)]

@@ -323,3 +323,33 @@ def test_objective_chain_restatement(oracle):
     mask = np.array([1, 5, P.n], dtype=np.int32)
     g = oracle.mask_exterior_const(x + 1.0, mask, -1.0)
     assert g[0] == x[0] + 1.0 and g[4] == x[4] + 1.0 and g[-1] == x[-1] + 1.0 and np.all(np.delete(g, [0, 4, P.n - 1]) == -1.0)
+
+
+def test_helmholtz_operator_restatement(oracle):
+    """Neko ax_helm restated in oracle.c: the assembled operator r^2 K + M on a deformed mesh is symmetric
+    positive definite, K annihilates constants (A 1 = M 1), <u, K u> equals the Dirichlet integral of a known
+    field on an affine mesh, and the dense PDE-filter solve leaves constants fixed and contracts the range."""
+    from helpers import Problem
+    lx = 5
+    P = Problem(lx, ne=(2, 2, 1), deform=0.04)
+    cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
+    jacinv = 1.0 / P.jac
+    rep = np.unique(cid, return_index=True)[1]
+    A = np.zeros((nc, nc))
+    for k in range(nc):
+        e = (cid == k).astype(np.float64)
+        A[:, k] = oracle.gs_add(oracle.ax_helm(e, lx, P.nelv, P.D, P.w, P.G, jacinv, P.B, 0.3, 1.0), cid, nc)[rep]
+    assert np.abs(A - A.T).max() <= 1e-12 * np.abs(A).max()
+    assert np.linalg.eigvalsh(0.5 * (A + A.T)).min() > 0.0
+    one = np.ones(P.n)
+    a1 = oracle.ax_helm(one, lx, P.nelv, P.D, P.w, P.G, jacinv, P.B, 0.3, 1.0)
+    assert np.abs(a1 - P.B).max() <= 1e-12
+    Q = Problem(7, ne=(2, 2, 2), deform=0.0)
+    x, y, z = [a.reshape(-1).numpy() for a in Q.xyz]
+    u = np.sin(2.0 * x) + y * z
+    Ku = oracle.ax_helm(u, 7, Q.nelv, Q.D, Q.w, Q.G, 1.0 / Q.jac, Q.B, 1.0, 0.0)
+    exact = (2.0 + 0.5 * np.sin(4.0)) + 1.0 / 3.0 + 1.0 / 3.0      # int 4cos^2(2x) + z^2 + y^2 over the unit cube
+    assert abs(float(u @ Ku) - exact) <= 1e-7
+    xf = oracle.pde_filter_dense(P.rho, lx, P.nelv, P.D, P.w, P.G, jacinv, P.B, cid, nc, 0.1)
+    assert P.rho.min() < xf.min() and xf.max() < P.rho.max()
+    assert np.abs(oracle.pde_filter_dense(one, lx, P.nelv, P.D, P.w, P.G, jacinv, P.B, cid, nc, 0.1) - 1.0).max() <= 1e-12

@@ -68,8 +68,8 @@ __global__ void gs_classid_kernel(const int* __restrict__ rep, const int* __rest
 // UN classes per thread are in flight together (every class has >= 2 members, so the first two members of
 // each are gathered unconditionally; the rare longer classes finish in a loop): the pass is bound by the
 // latency of the chain offsets -> members -> values, not by bandwidth.
-template <int NF, int UN = 2>
-__global__ void gs_op_kernel(double* f0, double* f1, double* f2,
+template <int NF, int UN = 1, int MINB = 3>
+__global__ void __launch_bounds__(256, MINB) gs_op_kernel(double* f0, double* f1, double* f2,
                              const int* __restrict__ off, const int* __restrict__ dof, int nclass,
                              const unsigned char* __restrict__ skip = nullptr) {
   const int stride = gridDim.x * blockDim.x;

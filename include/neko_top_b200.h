@@ -260,14 +260,16 @@ int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof,
 int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* bnd_elem);
 
 /* Processing order of the elements in the fused step (a permutation of 0..nelv-1, HOST; *nelem = 0
- * restores 0..nelv-1).  Results do not depend on it; speed does: b200_adjrhs_step sums the node classes
- * inside the element kernel as soon as all their member elements are stored, which only pays while the
- * earlier members are still in L2 -- neighbouring elements should be close in this order (for a structured
- * box: columns of 16x16 elements; bench.py / workloads.tile_order).  Neko's mesh order is arbitrary, so
- * the order is an input, exactly like the partition. */
+ * restores 0..nelv-1).  Results do not depend on it.  It only matters for the opt-in in-kernel summation
+ * (b200_adjrhs_set_gs_fused), which pays only while the earlier members of a node class are still in L2 --
+ * neighbouring elements should then be close in this order (workloads.tile_order); with the default separate
+ * gather-scatter pass the mesh order is best (the element-list variant of the kernel is ~10 % slower). */
 int b200_adjrhs_set_element_order(void* handle, const int* nelem, const int* order);
-/* *flag = 0: b200_adjrhs_step keeps the separate gather-scatter pass (default 1; environment
- * B200_GS_FUSED=0 does the same at create time).  Both paths give bit-identical results. */
+/* How b200_adjrhs_step sums the node classes (all three give bit-identical results):
+ *   *flag = 0 (default)  separate pass over the CSR class lists (fastest measured);
+ *   *flag > 0            inside the lx = 8 element kernel while f is still in L2 (experimental: removes the
+ *                        pass's DRAM traffic but is L1-bound and slower; environment B200_GS_FUSED=1);
+ *   *flag < 0            separate pass over the class lists packed by size (environment B200_GS_MODE=1). */
 int b200_adjrhs_set_gs_fused(void* handle, const int* flag);
 /* *fused = 1 if b200_adjrhs_step currently sums node classes inside the element kernel;
  * *classes_in_kernel of *classes_total are handled there (the rest: shared-node path, > 16 members). */

@@ -842,7 +842,7 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   const char* c = getenv("B200_ADJRHS_CFG");
   h->cfg = c ? atoi(c) : -1;
   const char* g = getenv("B200_GS_FUSED");
-  if (g) h->gs_mode = atoi(g) != 0 ? 2 : 1;
+  if (g) h->gs_mode = atoi(g) != 0 ? 2 : 0;
   g = getenv("B200_GS_MODE");
   if (g) h->gs_mode = std::min(2, std::max(0, atoi(g)));
   g = getenv("B200_EXCHANGE_OVERLAP");
@@ -1134,7 +1134,7 @@ int b200_adjrhs_set_element_order(void* handle, const int* nelem, const int* ord
 
 int b200_adjrhs_set_gs_fused(void* handle, const int* flag) {
   if (!handle || !flag) return fail(B200_ERR_ARG, "set_gs_fused: null argument");
-  H(handle)->gs_mode = (*flag > 0) ? 2 : (*flag < 0 ? 0 : 1);
+  H(handle)->gs_mode = (*flag > 0) ? 2 : (*flag < 0 ? 1 : 0);
   return B200_OK;
 }
 

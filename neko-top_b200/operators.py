@@ -499,12 +499,12 @@ class fused_adjoint_rhs_t:
         check(_lib.lib().b200_adjrhs_set_element_order(self._hd.h, _ci(o.size), o.ctypes.data_as(C.POINTER(C.c_int))))
 
     def set_gs_fused(self, flag=True):
-        """True: sum the node classes inside the v3 element kernel (experimental); False: separate pass."""
-        self.set_gs_mode(2 if flag else 1)
+        """True: sum the node classes inside the v3 element kernel (experimental); False: separate CSR pass."""
+        self.set_gs_mode(2 if flag else 0)
 
     def set_gs_mode(self, mode):
-        """2: inside the element kernel, 1: separate pass over the packed class lists (default), 0: CSR kernels."""
-        check(_lib.lib().b200_adjrhs_set_gs_fused(self._hd.h, _ci({2: 1, 1: 0, 0: -1}[int(mode)])))
+        """0: separate CSR pass (default), 1: separate pass over the packed class lists, 2: inside the element kernel."""
+        check(_lib.lib().b200_adjrhs_set_gs_fused(self._hd.h, _ci({2: 1, 1: -1, 0: 0}[int(mode)])))
 
     def gs_info(self):
         """(fused, classes summed inside the element kernel, classes in total)."""

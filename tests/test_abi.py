@@ -89,3 +89,44 @@ def test_c99_consumer_links_and_runs(L):
     assert out.returncode == 0, out.stderr
     from neko_top_b200 import _lib
     assert f"{len(_lib.SYMBOLS)} entry points" in out.stdout
+
+
+def test_fortran_shim_is_well_formed():
+    """No Fortran compiler exists in the image, so the shim gets a structural lint instead: every
+    subroutine / function / interface / module / type block is closed by a matching `end`, every bind(c) name
+    is an entry point of the header, and continuation lines are consistent."""
+    fdir = os.path.join(ROOT, "neko-top_b200", "fortran")
+    for fn in sorted(os.listdir(fdir)):
+        txt = open(os.path.join(fdir, fn)).read()
+        code = [re.sub(r"!.*$", "", ln).strip().lower() for ln in txt.splitlines()]
+        stack = []
+        joined, cur = [], ""
+        for ln in code:                                   # join continuation lines
+            if not ln:
+                continue
+            cur += " " + ln.rstrip("&").lstrip("&")
+            if not ln.endswith("&"):
+                joined.append(cur.strip())
+                cur = ""
+        assert cur == "", f"{fn}: dangling continuation"
+        for ln in joined:
+            m = re.match(r"end\s*(subroutine|function|interface|module|type|select|if|do|associate)\b", ln)
+            if m:
+                kind = m.group(1)
+                if kind in ("subroutine", "function", "interface", "module", "type"):
+                    assert stack and stack[-1] == kind, f"{fn}: unexpected 'end {kind}' (open: {stack[-3:]})"
+                    stack.pop()
+                continue
+            if re.match(r"(abstract\s+)?interface\b", ln):
+                stack.append("interface")
+            elif re.match(r"module\s+(?!procedure)\w+$", ln):
+                stack.append("module")
+            elif re.match(r"type\s*(,[^:]*)?::\s*\w+$", ln) or re.match(r"type\s+\w+$", ln):
+                stack.append("type")
+            elif re.search(r"\bsubroutine\s+\w+\s*\(", ln) and not ln.startswith("call"):
+                stack.append("subroutine")
+            elif re.search(r"\bfunction\s+\w+\s*\(", ln) and "end function" not in ln:
+                stack.append("function")
+        assert not stack, f"{fn}: unclosed blocks {stack}"
+        for name in re.findall(r"bind\s*\(\s*c\s*,\s*name\s*=\s*'([^']+)'", txt):
+            assert name in _lib.SYMBOLS, f"{fn}: bind(c) name {name} is not in the header"

@@ -364,7 +364,8 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
+            "metric": METRIC if lx == 8 else METRIC.replace("lx=8", f"lx={lx}"), "value": value, "unit": UNIT,
+            "n_gpus": N, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(ne, lx, N), "lx": lx, "elements_per_gpu": ne ** 3,

@@ -96,3 +96,20 @@ def test_reference_pipe_mesh_fixture():
         assert np.unique(np.stack([keys, by_coord.reshape(-1)], 1), axis=0).shape[0] == nnode
         _, jac, B = sem.geometric_factors(x, y, z, sem.Space(lx))
         assert float(jac.min()) > 0.0 and abs(float(B.sum()) - 10.0) < 1e-12
+
+
+def test_tile_order_is_a_permutation_with_short_reach():
+    """workloads.tile_order: a permutation of the elements; inside a tile column the z-neighbour of an element is
+    exactly tx*ty positions later and the x-neighbour is adjacent."""
+    import numpy as np
+    from neko_top_b200 import workloads
+    b = workloads.BoxBrick(lx=8, ne=(12, 8, 5))
+    o = workloads.tile_order(b, (4, 4))
+    assert sorted(o.tolist()) == list(range(b.nelv))
+    pos = np.empty(b.nelv, dtype=np.int64)
+    pos[o] = np.arange(b.nelv)
+    e = lambda x, y, z: x + 12 * (y + 8 * z)
+    assert pos[e(1, 0, 0)] - pos[e(0, 0, 0)] == 1
+    assert pos[e(0, 1, 0)] - pos[e(0, 0, 0)] == 4
+    assert pos[e(0, 0, 1)] - pos[e(0, 0, 0)] == 16
+    assert pos[e(4, 0, 0)] - pos[e(0, 0, 0)] == 16 * 5          # next tile column

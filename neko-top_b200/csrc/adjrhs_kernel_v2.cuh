@@ -317,6 +317,8 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
           fi2 = ustage[(R_FIN - NGEO + 2) * UF + pl];
         }
       }
+      // the stage is in registers: order these generic-proxy reads before the async-proxy refill, then release
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&sbar[st * 2 + 1]);
       if (++st == NS) { st = 0; ph ^= 1; }

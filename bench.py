@@ -51,6 +51,24 @@ def workload_name(ne, lx, n):
     return f"{tag}: synthetic box {ne}^3 hex elements per GPU, lx={lx}, random design field rho"
 
 
+def config_dict(args):
+    """`config` of the JSON line: the same dict, key for key, from both arms (b200 and --impl reference)."""
+    from neko_top_b200 import workloads
+    n = args.lx ** 3 * args.ne ** 3
+    return {"workload": workload_name(args.ne, args.lx, args.gpus), "lx": args.lx,
+            "elements_per_gpu": args.ne ** 3, "dof_per_gpu": n,
+            "rank_grid": list(workloads.rank_grid(args.gpus)),
+            "l2": "inputs (21 fields, %.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (21 * n * 8 / 1e9)}
+
+
+def host_cores():
+    """Host cores this process may use (torch.distributed.run exports OMP_NUM_THREADS=1: ignored on purpose)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:      # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks: sampled with NVML from a thread DURING the timed region
 # ------------------------------------------------------------------------------------------------
@@ -131,9 +149,10 @@ def cpu_sample_problem(ne_gpu, lx, sample_ne, px=1, py=1, pz=1):
                                                 f"({brick.n} DOF per step)")
 
 
-def time_oracle(prob, steps, warmup, budget_s=None):
+def time_oracle(prob, steps, warmup, budget_s=None, keep=None):
     from oracle import pyoracle as orc
     orc.build()
+    orc.set_num_threads(host_cores())
     b = prob["brick"]
     st = orc.RhsStep(prob["v"], prob["ub"], prob["rho"], b.lx, b.nelv, prob["sp"].dx, prob["sp"].wx, prob["G"],
                      prob["B"], prob["key"])
@@ -147,7 +166,43 @@ def time_oracle(prob, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    if keep is not None:
+        keep["f"], keep["sens"] = st.f, st.sens
     return b.n * done / dt / 1e9, dt / done * 1e3, done, orc.num_threads()
+
+
+def parity_vs_oracle(prob, f_dev, sens_dev, ne_gpu, oracle_out=None, tol=1e-12):
+    """The GPU step's result on the corner sample against the oracle's on the same inputs.  The oracle sees the
+    sample as a mesh of its own, so direct-stiffness sums are comparable on the nodes whose class lies inside
+    the sample (not on its cut faces); the sensitivity is point-wise and compared everywhere."""
+    import numpy as np
+    import torch
+    b = prob["brick"]
+    s, lx, N = b.ne[0], b.lx, b.lx ** 3
+    if oracle_out is None:
+        oracle_out = {}
+        time_oracle(prob, 1, 0, keep=oracle_out)
+    e = torch.arange(b.nelv)
+    ex, ey, ez = e % s, (e // s) % s, e // (s * s)
+    idx = (ex + ne_gpu * (ey + ne_gpu * ez)).to(f_dev[0].device)
+    p = torch.arange(lx)
+    cut = []
+    for d, (el, pt) in enumerate(((ex, p.view(1, 1, 1, lx)), (ey, p.view(1, 1, lx, 1)), (ez, p.view(1, lx, 1, 1)))):
+        g = (el * (lx - 1)).view(-1, 1, 1, 1) + pt
+        on_cut = (g == s * (lx - 1)) if s < b.ne_global[d] else torch.zeros_like(g, dtype=torch.bool)
+        cut.append(on_cut.expand(b.nelv, lx, lx, lx))
+    inside = ~(cut[0] | cut[1] | cut[2]).reshape(-1).numpy()
+    rel = lambda a, r: float(np.linalg.norm(a - r) / max(np.linalg.norm(r), 1e-300))
+    errs = []
+    for c in range(3):
+        got = f_dev[c].view(-1, N)[idx].reshape(-1).cpu().numpy()
+        errs.append(rel(got[inside], oracle_out["f"][c][inside]))
+    es = rel(sens_dev.view(-1, N)[idx].reshape(-1).cpu().numpy(), oracle_out["sens"])
+    worst = max(max(errs), es)
+    return {"rel_l2_f": max(errs), "rel_l2_sens": es, "n_dof_checked": int(inside.sum()), "tol": tol,
+            "ok": bool(np.isfinite(worst) and worst <= tol),
+            "against": "oracle/oracle.c on the " + prob["desc"] + "; f after gs on the nodes whose class lies inside "
+                       "the sample, sens on all of it"}
 
 
 def run_reference(args):
@@ -162,8 +217,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.ne, args.lx, args.gpus), "lx": args.lx,
-                   "elements_per_gpu": args.ne ** 3},
+        "config": config_dict(args),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": prob["desc"] + "; oracle/oracle.c (OpenMP over elements); the Fortran/Neko "
                                                   "reference cannot be built in this image"},
@@ -208,7 +262,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import neko_top_b200  # noqa: F401
-    from neko_top_b200 import operators as ops, partition, sem, workloads
+    from neko_top_b200 import operators as ops, sem, workloads
 
     N = args.gpus
     rank = int(os.environ.get("RANK", "0"))
@@ -249,11 +303,11 @@ def run_b200(args):
         idb = [ops.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(idb, src=0)
         op.comm_init(idb[0], rank, N)
+        # shared-node discovery behind the C ABI (device sort + ncclAllGather); the candidate mask plays the role
+        # of Neko's dm_Xh%shared_dof
         cand = workloads.interface_candidates(brick, dev)
-        sh = partition.find_shared_nodes(keys, cand, lx ** 3, rank, N)
+        op.gs.init_shared_from_keys(keys, cand)
         del cand
-        op.gs.init_shared(sh.shared_dof, sh.neigh_rank, sh.neigh_off, sh.neigh_idx)
-        op.set_boundary_elements(sh.bnd_elem)
     del keys
     torch.cuda.empty_cache()
 
@@ -346,21 +400,36 @@ def run_b200(args):
             traffic = tj.get(f"ne{ne}_lx{lx}", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    xs_active, xs_linked, xs_left, xs_total = op.xstage_info()
+    if lx == 8:
+        kname = ("adjrhs_v3_kernel<3,4,2,14,168,XS> (fused element kernel, DMMA contractions, i-face pair classes "
+                 "summed in registers; 168 B/DOF algorithmic)") if xs_active else \
+                "adjrhs_v3_kernel<3,4,2,14,168> (fused element kernel, DMMA contractions; 168 B/DOF algorithmic)"
+    else:
+        kname = "adjrhs_v2_kernel (fused element kernel; 168 B/DOF algorithmic)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("adjrhs_v3_kernel<3,4,2,14,168> (fused element kernel, DMMA contractions; "
-                           "168 B/DOF algorithmic)") if lx == 8 else "adjrhs_v2_kernel (fused element kernel; 168 B/DOF algorithmic)",
+                "traffic_source": ("profiles/traffic.json (ncu --set full capture of this kernel at this size; not "
+                                   "re-measured in this run)") if traffic is not None else None,
+                "kernel": kname,
+                "gs_classes_in_pass": int(xs_left), "gs_classes_total": int(xs_total),
                 "kernel_ms": elem_ms, "gs_ms": gs_ms, "algorithmic_bytes_per_launch": n * bpd,
                 "peak_source": peak_src,
                 "step_GBps": n * sem.algorithmic_bytes_per_dof(lx, True) / (ms_step * 1e-3) / 1e9}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
-    if rank == 0 and N == 1 and not args.no_cpu:
-        prob = cpu_sample_problem(ne, lx, args.cpu_sample_ne)
-        cval, cms, cdone, threads = time_oracle(prob, 40, 2, budget_s=12.0)
-        cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": prob["desc"] + f"; {cdone} steps of oracle/oracle.c, {cms:.1f} ms each"}
+    parity = None
+    if rank == 0:
+        px, py, pz = workloads.rank_grid(N)
+        prob = cpu_sample_problem(ne, lx, args.cpu_sample_ne, px, py, pz)
+        kept = {}
+        if N == 1 and not args.no_cpu:
+            cval, cms, cdone, threads = time_oracle(prob, 40, 2, budget_s=12.0, keep=kept)
+            cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": prob["desc"] + f"; {cdone} steps of oracle/oracle.c, {cms:.1f} ms each"}
+        # ---- parity of THIS run's result (every N): the last timed step against the oracle ------------
+        parity = parity_vs_oracle(prob, f, sens, ne, oracle_out=kept or None)
 
     if rank == 0:
         line = {
@@ -368,12 +437,9 @@ def run_b200(args):
             "n_gpus": N, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(ne, lx, N), "lx": lx, "elements_per_gpu": ne ** 3,
-                       "dof_per_gpu": n, "rank_grid": list(workloads.rank_grid(N)), "host_cpus_bound": numa,
-                       "l2": "inputs (21 fields, %.1f GB per GPU) exceed the 126 MB L2; no flush needed"
-                             % (21 * n * 8 / 1e9)},
+            "config": config_dict(args),
             "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clk.summary(), "checksum_abs_f": checksum,
+            "parity": parity, "clocks": clk.summary(), "checksum_abs_f": checksum, "host_cpus_bound": numa,
         }
         if phases:
             names = (["boundary_elements", "shared_gs", "pack", "interior_elements", "local_gs", "wait_recv+unpack"]
@@ -385,6 +451,9 @@ def run_b200(args):
     if N > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        print(f"bench.py: PARITY FAILED: {parity}", file=sys.stderr, flush=True)
+        return 3
     return 0
 
 

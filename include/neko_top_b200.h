@@ -45,6 +45,8 @@ int64_t b200_launch_count(void);
 /* ---- handle: one per (space, mesh partition) == one per Neko `coef_t` -----------------------
  * replaces the state held by adv_lin_no_dealias_t (adjoint/adv_adjoint_no_dealias.f90:57-77)
  * and adv_lin_dealias_t (adjoint/adv_adjoint_dealias.f90:56-131). */
+/* *device: CUDA device index, or -1 (or NULL) = the calling thread's current device (what a Neko rank selected
+ * in device_init; use this from Fortran).  Every entry point makes the handle's device current. */
 int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int* device);
 int b200_adjrhs_free(void** handle);
 /* Neko enqueues everything on glb_cmd_queue (math_ext.cu:54); pass it here (NULL = default). */
@@ -256,6 +258,17 @@ int b200_comm_init(void* handle, const char* id128, const int* rank, const int* 
  *   shared_dof) of the nodes shared with it, in an order both sides agree on (ascending key). */
 int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof, const int* nneigh,
                         const int* neigh_rank, const int* neigh_off, const int* neigh_idx);
+/* Shared-node discovery behind the C ABI: what Neko's gs_t%init does from the dofmap
+ * (adjoint/adjoint_scheme.f90:339-343 `gs_Xh%init(dm_Xh)`).  Collective over the communicator of b200_comm_init;
+ * call after b200_gs_init with the SAME keys.  `cand` (n bytes, same memory space as `key`, may be NULL) flags
+ * the dofs that can live on another rank -- from Fortran: Neko's dm_Xh%shared_dof; NULL = every dof on the
+ * surface of its element (fine for small meshes, wasteful for large ones).  On the device: candidate keys are
+ * sorted and made unique (CUB), all-gathered with ncclAllGather, and every rank intersects its list with every
+ * other rank's; the per-neighbour message layout is the intersection in ascending key order, so both sides agree
+ * without a handshake.  Ends by calling b200_gs_init_shared and b200_adjrhs_set_boundary_elements with the lists
+ * it found.  *nshared / *nneigh (optional) return the number of shared nodes / neighbour ranks. */
+int b200_gs_init_shared_from_keys(void* handle, const int64_t* key, const int* on_device,
+                                  const unsigned char* cand, int* nshared, int* nneigh);
 /* elements that own a shared node (computed first so the exchange overlaps the interior ones) */
 int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* bnd_elem);
 
@@ -274,6 +287,18 @@ int b200_adjrhs_set_gs_fused(void* handle, const int* flag);
 /* *fused = 1 if b200_adjrhs_step currently sums node classes inside the element kernel;
  * *classes_in_kernel of *classes_total are handled there (the rest: shared-node path, > 16 members). */
 int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, int64_t* classes_total);
+/* "x stage" of the lx = 8 element kernel (default on; environment B200_XSTAGE=0 or *flag = 0 switches it off).
+ * In b200_adjrhs_step every element slot walks a contiguous run of elements; where consecutive elements e-1, e
+ * are glued i = lx-1 -> i = 0 node by node (verified against the classes of b200_gs_init) the kernel sums the
+ * face-interior pair classes in registers, and the gather-scatter pass that follows runs over the remaining
+ * classes only -- it then touches 44 % instead of 100 % of the 32-byte sectors of f.  a + b is commutative, so
+ * the result stays bit-identical to gs_op(GS_OP_ADD) after the plain kernel (adjoint_pnpn.f90:755-757).
+ * Used when the elements are in mesh order (no b200_adjrhs_set_element_order), gs mode 0, no point-zone mask. */
+int b200_adjrhs_set_xstage(void* handle, const int* flag);
+/* *active = 1 if the last/next b200_adjrhs_step uses it; *linked_elements = elements whose i = 0 face is summed
+ * in the kernel; *classes_left of *classes_total stay in the gather-scatter pass */
+int b200_adjrhs_xstage_info(void* handle, int* active, int64_t* linked_elements, int64_t* classes_left,
+                            int64_t* classes_total);
 
 /* ---- diagnostics ----------------------------------------------------------------------------*/
 /* average device time (ms) of the last fused element-kernel launches measured with CUDA events

@@ -23,8 +23,8 @@ SYMBOLS = [
     "b200_curl", "b200_curlcurl_forcing", "b200_min_dissipation_objective", "b200_mask_exterior_const", "b200_pde_filter_apply",
     "b200_sumab", "b200_makeabf", "b200_makebdf", "b200_makeabf_bdf",
     "b200_gs_init", "b200_gs_get_classes", "b200_gs_op", "b200_gs_op3",
-    "b200_comm_unique_id", "b200_comm_init", "b200_gs_init_shared",
-    "b200_adjrhs_set_boundary_elements", "b200_adjrhs_set_element_order", "b200_adjrhs_gs_info", "b200_adjrhs_set_gs_fused", "b200_adjrhs_enable_timing", "b200_adjrhs_get_timing", "b200_adjrhs_get_phase_timing",
+    "b200_comm_unique_id", "b200_comm_init", "b200_gs_init_shared", "b200_gs_init_shared_from_keys",
+    "b200_adjrhs_set_boundary_elements", "b200_adjrhs_set_element_order", "b200_adjrhs_gs_info", "b200_adjrhs_set_gs_fused", "b200_adjrhs_set_xstage", "b200_adjrhs_xstage_info", "b200_adjrhs_enable_timing", "b200_adjrhs_get_timing", "b200_adjrhs_get_phase_timing",
 ]
 
 

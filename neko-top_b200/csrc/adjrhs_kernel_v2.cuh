@@ -1,6 +1,6 @@
 // Fused adjoint-RHS element kernel for sm_100a (fp64), second generation ("v2").
 //
-// Same arithmetic as adjrhs_kernel.cuh (see the operator summary and the reference citations there);
+// Same arithmetic as every fused kernel (adjrhs_common.cuh: see the operator summary and the reference citations there);
 // what changes is how an SM is filled.  The first kernel ran 2 CTAs of (2 consumer warps + 1 TMA warp)
 // per SM: ncu showed DRAM traffic already at the algorithmic minimum but only 1.5 warps per scheduler,
 // 29 % issue utilisation and consumers waiting on plane data (profiles/README.md, r01a).  Here:
@@ -28,7 +28,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "adjrhs_kernel.cuh"   // PTX helpers, flags, wsw(), load_row/store_row
+#include "adjrhs_common.cuh"   // operator summary, flags, PTX helpers, wsw(), load_row/store_row
 
 namespace b200 {
 
@@ -63,6 +63,8 @@ struct KParams2 {
   unsigned long long* gs_done;  // one counter per window of nslots consecutive positions (zeroed per launch)
   int gs_lag;                 // windows between storing an element and summing its classes (>= 1)
   int elem_base;              // v2: added to every element index (field pointers stay 16-byte aligned for odd LX)
+  const unsigned char* xlink; // v3 XS: xlink[e] != 0: faces (e-1: i=7) and (e: i=0) are glued node by node
+  int xs_shift;               // v3 XS: log2 of the run length inside a window (>= 30: one contiguous run per slot)
 };
 
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {

@@ -27,7 +27,17 @@
 // (the plane's owner), so each warp runs its own ring of DS stages: wait on the stage's mbarrier, pull the 14
 // fields into registers, fence.proxy.async, and an elected lane re-arms the stage with the TMA bulk copies
 // (packed geometry image + point-wise fields) of the plane it will need DS planes later.
-// Arithmetic = adjrhs_kernel.cuh header.
+// Arithmetic = adjrhs_common.cuh header.
+//
+// XS ("x stage", profiles/README.md r02): the separate gather-scatter pass re-reads and re-writes ALL of f because
+// every 32-byte sector of an element holds a node of an i-face (i = 0 or 7).  With XS each slot processes a
+// CONTIGUOUS run of elements, and where element e-1 and e are glued i=7 -> i=0 with identical (j,k) orientation
+// (p.xlink[e], verified against the gather-scatter classes at set-up) the 36 face-interior pair classes are
+// summed here: lane (g,3) keeps the previous element's i = 7 values of its planes in shared memory, one
+// shfl.xor(3) pairs it with lane (g,0), which adds the partner to its i = 0 value before the regular store,
+// while lane (g,3) rewrites the previous element's i = 7 value (an 8-byte store into a line that is still in
+// L2).  a + b is commutative, so both copies are bit-identical to the oracle's (0 + a) + b.  The pass that
+// follows skips these classes and then touches only the rows j = 0,7 / planes k = 0,7: 44 % of the sectors.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,6 +59,9 @@ struct V3Cfg {
   static constexpr int SLOT_BYTES = WT_BYTES + SCR_BYTES + NW * DS * STAGE_BYTES;
   static constexpr int BAR_OFF = NE * SLOT_BYTES;
   static constexpr int SMEM = BAR_OFF + 8 * NE * NW * DS + 16;
+  static constexpr int X7_BYTES = 3 * 64 * 8;                // XS: previous element's i = 7 values [c][k][j]
+  static constexpr int SMEM_XS = SMEM + NE * X7_BYTES;
+  static_assert(SMEM % 16 == 0, "X7 area must stay 8-byte aligned");
   static_assert(8 % NW == 0, "NW must divide 8");
 };
 
@@ -86,16 +99,18 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 //     member count into pair / quad / oct / hex lists; gs_eoff[p] = first entry of position p in each list.
 //   * After storing its element of window w a slot publishes it: bar.sync (slot) -> thread 0:
 //     red.release.gpu.add(gs_done[w]).  Every GSB iterations it sums the classes that completed at ITS positions
-//     of the windows up to LAG before the newest: each warp polls the window counters (relaxed, L2) until the whole
+//     of the windows up to LAG before the newest: each warp polls the window counters (acquire, L2) until the whole
 //     window is stored, then gathers with ld.global.cg (L2, never a stale L1 line), adds the members in
 //     ascending dof order (the oracle's order: results are bit-identical to gs_op_kernel) and scatters.
 //     All CTAs are co-resident (grid <= #SMs, 1 CTA/SM) and every slot publishes window w before it waits
 //     for window w, so the wait cannot deadlock.
 //   * The streaming inputs are loaded with an L2 evict_first policy so that they do not push f out of L2
 //     before its classes complete (a z-neighbour in a 16x16-element tile column is 256 positions away).
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+// acquire at gpu scope: pairs with the publishers' red.release.gpu, so the gathers that follow the spin are
+// ordered after the stores of every slot counted in the value read
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 // publish: release-add at gpu scope (orders the slot's earlier stores, made visible to this thread by the
@@ -192,11 +207,34 @@ __device__ __forceinline__ void gs_batch(const KParams2<8>& p, int pos0, int nsl
   }
 }
 
+// element -> (slot, iteration) map of the XS kernels; shared with the set-up (capi.cu build_xstage)
+struct XsMap { int nfull, tail0, rem; };
+__host__ __device__ __forceinline__ XsMap xs_map(int nelem, int nslots, int shift) {
+  XsMap m;
+  const long long W = (long long)nslots << shift;           // elements per full window
+  m.nfull = (int)(nelem / W);
+  m.tail0 = (int)(m.nfull * W);
+  m.rem = nelem - m.tail0;
+  return m;
+}
+// true if element e is the first of a run (its predecessor e-1 is processed by another slot, or much earlier)
+__host__ __device__ __forceinline__ bool xs_is_run_start(int e, int nelem, int nslots, int shift) {
+  const XsMap m = xs_map(nelem, nslots, shift);
+  if (e < m.tail0) return (e & ((1 << shift) - 1)) == 0;
+  const int t = e - m.tail0;                                 // balanced runs of the tail: starts floor(s*rem/nslots)
+  const long long sidx = ((long long)t * nslots + m.rem - 1) / m.rem;
+  return (sidx * m.rem) / nslots == t;
+}
+
 // GS: compile the in-kernel summation in (FLAG_GS is then honoured); HINT: evict_first policy on the inputs
-template <int NE, int NW, int DS, int NF, int MAXREG, bool GS = false, bool HINT = false, bool LIST = false>
+template <int NE, int NW, int DS, int NF, int MAXREG, bool GS = false, bool HINT = false, bool LIST = false,
+          int XS = 0>
 __global__ void __launch_bounds__(V3Cfg<NE, NW, DS, NF>::NTHREADS, 1) __maxnreg__(MAXREG)
 adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   using C = V3Cfg<NE, NW, DS, NF>;
+  // XS = 1: exchange through shfl + shared memory; XS = 2: lane (g,0) re-loads the previous element's i = 7 value
+  // from L2 (__ldcg) and rewrites it -- no cross-lane traffic
+  static_assert(!XS || (!GS && !LIST), "the x stage runs on contiguous element runs without the in-kernel gs");
   constexpr int LX = 8, N = 512, PLANE = 64;
   constexpr int NPL = LX / NW;        // planes per warp
   constexpr int NTASK = 24;           // (component, j-slab) tasks of the t-direction stages
@@ -249,7 +287,23 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   const int scr_r0 = scr_off(g, q), scr_r1 = scr_off(g, q + 4);
 
   const int g0 = (int)blockIdx.x * NE + slot;
-  const int n_my = (p.nelem > g0) ? (p.nelem - 1 - g0) / nslots + 1 : 0;
+  // XS: slot g0 owns the contiguous run [e_first, e_first + n_my) (balanced to +-1 element); otherwise the
+  // elements g0, g0 + nslots, ... (the grid works on a window of nslots consecutive elements)
+  [[maybe_unused]] int e_first = 0, xs_full = 0;
+  int n_my_;
+  if constexpr (XS) {
+    // windows of nslots runs of R = 2^xs_shift consecutive elements (neighbouring slots stay close in memory);
+    // the elements after the last full window are shared out as one balanced contiguous run per slot
+    const XsMap m = xs_map(p.nelem, nslots, p.xs_shift);
+    xs_full = m.nfull << p.xs_shift;                                      // iterations inside full windows
+    e_first = m.tail0 + (int)(((long long)g0 * m.rem) / nslots);          // first element of the tail run
+    n_my_ = xs_full + (int)(((long long)(g0 + 1) * m.rem) / nslots) - (e_first - m.tail0);
+  } else {
+    n_my_ = (p.nelem > g0) ? (p.nelem - 1 - g0) / nslots + 1 : 0;
+  }
+  const int n_my = n_my_;
+  [[maybe_unused]] double* x7 = nullptr;
+  if constexpr (XS == 1) x7 = reinterpret_cast<double*>(smem + C::SMEM + slot * C::X7_BYTES);
   const int n_planes = n_my * NPL;               // planes this warp will consume
   const uint32_t stage_tx = (uint32_t)p.n_active * C::PLANE_BYTES;
 
@@ -262,6 +316,10 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     if constexpr (LIST) { if (itx < n_my) en = __ldg(p.elem_list + en); }
     return en;
   };
+  auto xs_elem = [&](int itx) {
+    if (itx >= xs_full) return e_first + (itx - xs_full);
+    return (((itx >> p.xs_shift) * nslots + g0) << p.xs_shift) + (itx & ((1 << p.xs_shift) - 1));
+  };
   [[maybe_unused]] int it_now = 0;
   [[maybe_unused]] int e_cur = 0, e_nxt = 0;
   if constexpr (LIST) { e_cur = elem_at(0); e_nxt = elem_at(1); }
@@ -270,6 +328,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     const int itn = n / NPL, pin = n - itn * NPL;      // itn is it_now or it_now + 1 (DS <= NPL)
     int en;
     if constexpr (LIST) en = (itn == it_now) ? e_cur : e_nxt;
+    else if constexpr (XS) en = xs_elem(itn);
     else en = g0 + itn * nslots;
     const size_t goff = (size_t)en * N + (size_t)(wid + pin * NW) * PLANE;
     unsigned char* dst = ring + (n % DS) * C::STAGE_BYTES;
@@ -313,7 +372,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
         for (int w = gs_sum; w < gs_sum + nw; w++) {
           const int rest = p.nelem - w * nslots;
           const unsigned long long want = (unsigned long long)(rest < nslots ? rest : nslots);
-          while (ld_volatile_u64(p.gs_done + w) < want) __nanosleep(64);
+          while (ld_acquire_u64(p.gs_done + w) < want) __nanosleep(64);
         }
       }
       __syncwarp();
@@ -325,8 +384,13 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   for (int it = 0; it < n_my; it++) {
     int e;
     if constexpr (LIST) { it_now = it; e = e_cur; }
+    else if constexpr (XS) e = xs_elem(it);
     else e = g0 + it * nslots;
     const size_t ebase = (size_t)e * N;
+    // xlink[e] != 0: e's i = 0 face is glued to the i = 7 face of element e-1, and e-1 is the element this slot
+    // processed in its previous iteration (the set-up knows the runs: xs_is_run_start)
+    [[maybe_unused]] bool xlinked = false;
+    if constexpr (XS) xlinked = (__ldg(p.xlink + e) != 0);
 
     // ---- t-derivatives of the base flow, per (component, j) slab -> Wt --------------------------------
 #pragma unroll
@@ -388,6 +452,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       if (pi == 0 && wid == 0 && it + 1 < n_my) {   // L2 prefetch of the slot's next base-flow element
         int en;
         if constexpr (LIST) en = e_nxt;
+        else if constexpr (XS) en = xs_elem(it + 1);
         else en = g0 + (it + 1) * nslots;
         if (elect_one()) {
 #pragma unroll
@@ -511,12 +576,37 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
 #pragma unroll
     for (int pi = 0; pi < NPL; pi++) {
       const int k = wid + pi * NW;
+      [[maybe_unused]] double pv[3];
+      [[maybe_unused]] bool xdo = false;
+      [[maybe_unused]] size_t xoff = 0;
+      if constexpr (XS == 2) {
+        xdo = xlinked && q == 0 && g >= 1 && g <= 6 && k >= 1 && k <= 6;
+        xoff = ebase - N + 64 * k + 8 * g + 7;          // (i = 7, j = g, k) of the slot's previous element
+        if (xdo) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) pv[c] = __ldcg(p.f[c] + xoff);
+        }
+      }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const double2 rt = *reinterpret_cast<const double2*>(Wt + c * N + wt_off(2 * q, g, k));
         double2 o;
         o.x = cacc[pi][c].x + rt.x;
         o.y = cacc[pi][c].y + rt.y;
+        if constexpr (XS == 1) {
+          // lanes (g,0) and (g,3) swap: this element's i = 0 value against the previous element's i = 7 value
+          double* slot7 = x7 + c * 64 + k * 8 + g;
+          const double mine = (q == 3) ? *slot7 : o.x;
+          const double other = __shfl_xor_sync(0xffffffffu, mine, 3);
+          if (xlinked && g >= 1 && g <= 6 && k >= 1 && k <= 6) {
+            if (q == 0) o.x += other;
+            if (q == 3) p.f[c][ebase - N + 64 * k + 8 * g + 7] = mine + other;
+          }
+          if (q == 3) *slot7 = o.y;
+        }
+        if constexpr (XS == 2) {
+          if (xdo) { o.x += pv[c]; p.f[c][xoff] = o.x; }
+        }
         *reinterpret_cast<double2*>(p.f[c] + ebase + 64 * k + pl2) = o;
       }
     }

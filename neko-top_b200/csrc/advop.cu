@@ -31,11 +31,15 @@ cudaError_t launch_one(const AdvLaunch& a) {
   for (int c = 0; c < 3; c++) { p.v[c] = a.v[c]; p.vb[c] = a.vb[c]; p.f[c] = a.f[c]; p.fs[c] = a.fs[c]; }
   for (int g = 0; g < 9; g++) p.G[g] = a.G[g];
   p.rho = a.rho; p.B = a.B; p.sens = a.sens; p.chi_out = a.chi_out;
-  p.elem_list = a.elem_list; p.nelem = a.nelem; p.flags = a.flags;
+  p.elem_list = a.elem_list; p.nelem = a.nelem; p.elem_base = a.elem_base; p.flags = a.flags;
   p.f_min = a.f_min; p.f_max = a.f_max; p.q = a.q; p.K_lube = a.K_lube; p.K_sens = a.K_sens;
   auto kern = advop_kernel<LX, LXD, MODE, MAXREG>;
-  static int per_sm = 0;   // per instantiation
-  if (!per_sm) {
+  static int per_sm = 0;   // per instantiation; the function attributes are per device
+  static unsigned long long dev_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !(dev_done >> dev & 1ull)) {
+    if (dev < 64) dev_done |= 1ull << dev;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -23,6 +23,7 @@ struct AdvLaunch {
   double* chi_out;
   const int* elem_list;
   int nelem;
+  int elem_base;                // first element when elem_list == NULL (chunked host-buffer step)
   unsigned flags;
   double f_min, f_max, q, K_lube, K_sens;
   int num_sm;

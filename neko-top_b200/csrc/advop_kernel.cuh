@@ -22,7 +22,7 @@
 //   phase 2  f_c -= (J^T x J^T x J^T) R_c                             map(., Xh_GLL) + sub2 (:384-392)
 //            (the reference projects six times; projection is linear, so once per component here)
 // With FLAG_ACCUM f is in/out (the advection_adjoint_t contract); otherwise the epilogue also evaluates the
-// point-wise part of the fused right-hand side (adjrhs_kernel.cuh header) at the GLL point and f is
+// point-wise part of the fused right-hand side (adjrhs_common.cuh header) at the GLL point and f is
 // write-only.
 //
 // Data flow: r/s contractions read shared memory (D rows in registers would not fit beside the 3*LXD
@@ -34,7 +34,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "adjrhs_kernel.cuh"   // FLAG_*
+#include "adjrhs_common.cuh"   // FLAG_*
 #include "advop.h"           // ADV_ADJOINT / ADV_LINEAR
 
 namespace b200 {
@@ -55,6 +55,7 @@ struct AdvParams {
   double* chi_out;
   const int* elem_list;
   int nelem;
+  int elem_base;                // first element of a contiguous range (elem_list == NULL)
   unsigned flags;
   double f_min, f_max, q, K_lube, K_sens;
 };
@@ -204,7 +205,7 @@ advop_kernel(const __grid_constant__ AdvParams<LX, LXD> p) {
   __syncthreads();
 
   for (int it = blockIdx.x; it < p.nelem; it += gridDim.x) {
-    const int e = p.elem_list ? __ldg(p.elem_list + it) : it;
+    const int e = p.elem_list ? __ldg(p.elem_list + it) : p.elem_base + it;
     const size_t eb = (size_t)e * N, ebd = (size_t)e * ND;
 
     // ---- phase 0: the six fields on the fine grid ----------------------------------------------------

@@ -16,10 +16,11 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
-#include "adjrhs_kernel.cuh"
 #include "adjrhs_kernel_v2.cuh"
 #include "adjrhs_kernel_v3.cuh"
 #include "advop.h"
@@ -63,6 +64,16 @@ int fail(int code, const char* fmt, ...) {
                   ncclGetErrorString(r_));                                                        \
   } while (0)
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// NVTX ranges named after the reference's profiler regions (Neko's profiler_start_region is nvtxRangePush on
+// the CUDA backend): 'Fluid' (adjoint/adjoint_pnpn.f90:639) holds the RHS construction, 'Velocity residual'
+// (:746) the gs_op at :755-757.  Header-only NVTX3: a no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 constexpr int LX_MAX = 10;
 
@@ -132,6 +143,20 @@ struct Handle {
   unsigned long long* sched_done = nullptr;
   std::vector<int> sched_elem_last;   // host copy: per position, the last position whose classes touch it (kind 1)
 
+  // x stage of the lx = 8 element kernel (adjrhs_kernel_v3.cuh XS): per-element link flags and the CSR lists
+  // of the classes that stay in the gather-scatter pass
+  int xs_enable = 1;               // B200_XSTAGE=0 switches it off
+  bool xs_valid = false;
+  int xs_nslots = 0;               // element slots of the grid the links were built for
+  int xs_shift = 3;                // runs of 2^xs_shift consecutive elements per slot and window (B200_XS_RUN)
+  int xs_variant = 2;              // B200_XS_VARIANT: 1 = shfl + shared memory, 2 = re-load from L2
+  int xs_nolink = 0;               // B200_XS_NOLINK=1 (diagnostic): same element map, no class summed in the kernel
+  unsigned char* xs_link = nullptr;
+  int *xs_off = nullptr, *xs_dof = nullptr;
+  unsigned char* xs_skip = nullptr;
+  int xs_nclass = 0;
+  int64_t xs_nlinked = 0, xs_nmember = 0;
+
   // minimum-dissipation objective chain: six work fields (curl of curl) and reduction partials
   double* work6 = nullptr;
   double* d_partial = nullptr;
@@ -178,65 +203,8 @@ struct LaunchArgs {
   bool sources;
   bool no_dealias;         // un-fused GLL-grid drop-in: ignore the handle's dealias switch
   bool gs_in_kernel;       // sum the node classes inside the element kernel (needs a valid schedule)
+  bool xstage;             // v3 XS: contiguous runs per slot, i-face pair classes summed in the kernel
 };
-
-template <int LX, int PC, int NS, int NU, int MAXREG>
-int launch_cfg(Handle* h, const LaunchArgs& a) {
-  using L = SmemLayout<LX, PC, NS, NU>;
-  using C = KernelCfg<LX, PC, NS, NU>;
-  KParams<LX> p;
-  memset(&p, 0, sizeof p);
-  for (int i = 0; i < LX * LX; i++) p.D[i] = h->D[i];
-  for (int i = 0; i < LX; i++) p.w[i] = h->w[i];
-  const size_t eoff = (size_t)a.elem_begin * L::N;
-  for (int c = 0; c < 3; c++) p.ub[c] = a.vb[c] + eoff;
-  for (int i = 0; i < PF_COUNT; i++) { p.pf[i] = nullptr; p.pf_slot[i] = -1; }
-  unsigned flags = 0;
-  int np = 0;
-  auto add = [&](int slot, const double* ptr) { p.pf[slot] = ptr + eoff; p.pf_slot[slot] = np++; };
-  for (int c = 0; c < 3; c++) add(PF_VX + c, a.v[c]);
-  for (int g = 0; g < 9; g++) add(PF_G0 + g, h->G[g]);
-  const bool need_B = a.sources || a.fs[0];
-  if (need_B) add(PF_B, h->B);
-  if (a.sources) {
-    add(PF_RHO, a.rho);
-    flags |= FLAG_SOURCES;
-    if (!a.rho_is_chi) flags |= FLAG_RAMP;
-    if (h->convex_up) flags |= FLAG_CONVEX_UP;
-    if (h->if_lube && h->lube_mask_size == 0) flags |= FLAG_LUBE;
-    if (a.chi_out) flags |= FLAG_CHI_OUT;
-  }
-  if (a.fs[0]) { for (int c = 0; c < 3; c++) add(PF_FS0 + c, a.fs[c]); flags |= FLAG_FSTATIC; }
-  if (a.fin[0]) { for (int c = 0; c < 3; c++) add(PF_FIN0 + c, a.fin[c]); flags |= FLAG_ACCUM; }
-  if (a.sens) flags |= FLAG_SENS;
-  p.n_pf = np;
-  for (int c = 0; c < 3; c++) p.f[c] = a.f[c] + eoff;
-  p.sens = a.sens ? a.sens + eoff : nullptr;
-  p.chi_out = a.chi_out ? a.chi_out + eoff : nullptr;
-  p.elem_list = a.elem_list;
-  p.nelem = a.nelem;
-  p.flags = flags;
-  p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
-  p.K_sens = h->if_lube ? h->K_sens : 0.0;
-
-  auto kern = adjrhs_fused_kernel<LX, PC, NS, NU, MAXREG>;
-  const int smem = L::total(np);
-  static int smem_set = -1;   // per instantiation
-  if (smem > smem_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHREADS, smem));
-  if (per_sm < 1) return fail(B200_ERR_STATE, "fused kernel does not fit: lx=%d smem=%d", LX, smem);
-  int grid = std::min(a.nelem, h->num_sm * per_sm);
-  if (grid < 1) return B200_OK;
-  kern<<<grid, C::NTHREADS, smem, h->stream>>>(p);
-  LAUNCHED();
-  CK(cudaGetLastError());
-  return B200_OK;
-}
-
 
 // ---- second-generation kernel (adjrhs_kernel_v2.cuh): NE element slots + one TMA warp per SM ----------
 template <int LX, int NE, int NS, int NF, int MAXREG>
@@ -289,10 +257,10 @@ int launch_v2_cfg(Handle* h, const LaunchArgs& a) {
   p.K_sens = h->if_lube ? h->K_sens : 0.0;
 
   auto kern = adjrhs_v2_kernel<LX, NE, NS, NF, MAXREG>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // per instantiation, one bit per device (the attribute is per device)
+  if (h->device >= 64 || !(attr_set >> h->device & 1ull)) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
+    if (h->device < 64) attr_set |= 1ull << h->device;
   }
   const int grid = std::min((a.nelem + NE - 1) / NE, h->num_sm);
   if (grid < 1) return B200_OK;
@@ -352,6 +320,12 @@ int fill_params2_lx8(Handle* h, const LaunchArgs& a, KParams2<8>& p) {
   p.flags = flags;
   p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
   p.K_sens = h->if_lube ? h->K_sens : 0.0;
+  if (a.xstage) {
+    if (!h->xs_valid || a.elem_begin != 0 || a.nelem != h->nelv || a.elem_list)
+      return fail(B200_ERR_STATE, "internal: x stage without matching link flags");
+    p.xlink = h->xs_link;
+    p.xs_shift = h->xs_shift;
+  }
   if (a.gs_in_kernel) {
     if (!h->sched_valid || a.elem_begin != 0 || a.nelem != h->sched_nelem)
       return fail(B200_ERR_STATE, "internal: in-kernel gs without a matching schedule");
@@ -367,7 +341,8 @@ int fill_params2_lx8(Handle* h, const LaunchArgs& a, KParams2<8>& p) {
   return B200_OK;
 }
 
-template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST>
+constexpr int XS_NE = 3;   // element slots per CTA of the x-stage kernels (the default configuration)
+template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST, int XS = 0>
 int launch_v3_cfg2(Handle* h, const LaunchArgs& a);
 
 template <int NE, int NW, int DS, int NF, int MAXREG, bool GS = false, bool HINT = false>
@@ -376,23 +351,26 @@ int launch_v3_cfg(Handle* h, const LaunchArgs& a) {
   return launch_v3_cfg2<NE, NW, DS, NF, MAXREG, GS, HINT, false>(h, a);
 }
 
-template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST>
+template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST, int XS>
 int launch_v3_cfg2(Handle* h, const LaunchArgs& a) {
   using C = V3Cfg<NE, NW, DS, NF>;
   if (a.gs_in_kernel != GS) return fail(B200_ERR_STATE, "internal: v3 kernel variant / gs_in_kernel mismatch");
-  static_assert(C::SMEM <= 227 * 1024, "v3 configuration exceeds the shared memory of an SM");
+  if (a.xstage != (XS != 0)) return fail(B200_ERR_STATE, "internal: v3 kernel variant / x stage mismatch");
+  constexpr int SMEM = (XS == 1) ? C::SMEM_XS : C::SMEM;
+  static_assert(SMEM <= 227 * 1024, "v3 configuration exceeds the shared memory of an SM");
   static_assert(C::NTHREADS <= 1024, "v3 configuration exceeds 1024 threads");
   static_assert(C::NTHREADS * MAXREG <= 65536, "v3 configuration exceeds the register file");
   KParams2<8> p;
   if (int r = fill_params2_lx8<NF>(h, a, p)) return r;
-  auto kern = adjrhs_v3_kernel<NE, NW, DS, NF, MAXREG, GS, HINT, LIST>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
+  auto kern = adjrhs_v3_kernel<NE, NW, DS, NF, MAXREG, GS, HINT, LIST, XS>;
+  static unsigned long long attr_set = 0;   // per instantiation, one bit per device (the attribute is per device)
+  if (h->device >= 64 || !(attr_set >> h->device & 1ull)) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (h->device < 64) attr_set |= 1ull << h->device;
   }
   const int grid = std::min((a.nelem + NE - 1) / NE, h->num_sm);
   if (grid < 1) return B200_OK;
+  if (XS && grid * NE != h->xs_nslots) return fail(B200_ERR_STATE, "internal: x-stage links built for another grid");
   if (a.gs_in_kernel) {
     // one completion counter per window of grid*NE positions; the spin-wait needs every CTA resident
     int per_sm = 0;
@@ -401,7 +379,7 @@ int launch_v3_cfg2(Handle* h, const LaunchArgs& a) {
     const int nwin = (a.nelem + grid * NE - 1) / (grid * NE);
     CK(cudaMemsetAsync(h->sched_done, 0, sizeof(unsigned long long) * nwin, h->stream));
   }
-  kern<<<grid, C::NTHREADS, C::SMEM, h->stream>>>(p);
+  kern<<<grid, C::NTHREADS, SMEM, h->stream>>>(p);
   LAUNCHED();
   CK(cudaGetLastError());
   return B200_OK;
@@ -416,6 +394,15 @@ int launch_v3(Handle* h, const LaunchArgs& a) {
 // the default configuration: also built with the in-kernel direct-stiffness summation
 int launch_v3_default(Handle* h, const LaunchArgs& a) {
   const bool full = a.fs[0] || a.fin[0];
+  if (a.xstage) {
+    if (a.gs_in_kernel || a.elem_list) return fail(B200_ERR_STATE, "internal: x stage with in-kernel gs / element list");
+    if (h->xs_variant == 1) {
+      if (full) return launch_v3_cfg2<XS_NE, 4, 1, NF_FULL, 168, false, false, false, 1>(h, a);
+      return launch_v3_cfg2<XS_NE, 4, 2, NF_FUSED, 168, false, false, false, 1>(h, a);
+    }
+    if (full) return launch_v3_cfg2<XS_NE, 4, 1, NF_FULL, 168, false, false, false, 2>(h, a);
+    return launch_v3_cfg2<XS_NE, 4, 2, NF_FUSED, 168, false, false, false, 2>(h, a);
+  }
   if (!a.gs_in_kernel) {
     if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168>(h, a);
     return launch_v3_cfg<3, 4, 2, NF_FUSED, 168>(h, a);
@@ -427,8 +414,6 @@ int launch_v3_default(Handle* h, const LaunchArgs& a) {
   if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168, true, false>(h, a);
   return launch_v3_cfg<3, 4, 2, NF_FUSED, 168, true, false>(h, a);
 }
-
-int launch_fused_v1(Handle* h, const LaunchArgs& a);
 
 // fine-grid operators (advop_kernel.cuh): dealiased adjoint / linearised advection, GLL-grid linearised
 int launch_fine(Handle* h, const LaunchArgs& a, int mode, bool dealias) {
@@ -462,7 +447,7 @@ int launch_fine(Handle* h, const LaunchArgs& a, int mode, bool dealias) {
     if (a.sens) flags |= FLAG_SENS;
   }
   L.B = h->B; L.sens = a.sens; L.chi_out = a.chi_out;
-  L.elem_list = a.elem_list; L.nelem = a.nelem; L.flags = flags;
+  L.elem_list = a.elem_list; L.nelem = a.nelem; L.elem_base = a.elem_list ? 0 : a.elem_begin; L.flags = flags;
   L.f_min = h->f_min; L.f_max = h->f_max; L.q = h->q; L.K_lube = h->K_lube;
   L.K_sens = h->if_lube ? h->K_sens : 0.0;
   L.num_sm = h->num_sm; L.stream = h->stream;
@@ -479,7 +464,6 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
   if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
   if (h->dealias_fused && !a.no_dealias) return launch_fine(h, a, ADV_ADJOINT, true);
   const int cfg = h->cfg;
-  if (cfg >= 100) return launch_fused_v1(h, a);
   switch (h->lx) {
     case 4: return launch_v2<4, 8, 4, 224>(h, a);
     // lx != 8 (v2): configurations from the r01j sweep (tools/lxsweep.py, profiles/r01j_lxsweep.jsonl).  What
@@ -508,29 +492,6 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
       }
     case 9: return cfg == 32 ? launch_v2<9, 3, 2, 200>(h, a) : launch_v2<9, 2, 4, 255, 2, 2>(h, a);
     case 10: return launch_v2<10, 2, 2, 224>(h, a);
-    default: return fail(B200_ERR_ARG, "lx=%d not instantiated (4..10)", h->lx);
-  }
-}
-
-int launch_fused_v1(Handle* h, const LaunchArgs& a) {
-  const int cfg = h->cfg - 100;
-  switch (h->lx) {
-    case 4: return launch_cfg<4, 2, 2, 2, 224>(h, a);
-    case 5: return launch_cfg<5, 1, 3, 2, 224>(h, a);
-    case 6: return launch_cfg<6, 2, 2, 2, 224>(h, a);
-    case 7: return launch_cfg<7, 1, 3, 2, 224>(h, a);
-    case 8:
-      switch (cfg) {
-        case 1: return launch_cfg<8, 4, 2, 2, 224>(h, a);   // 104 KB, 2 CTA/SM
-        case 2: return launch_cfg<8, 2, 3, 1, 224>(h, a);   //  78 KB, 2 CTA/SM
-        case 3: return launch_cfg<8, 1, 4, 1, 224>(h, a);   //  64 KB, 3 CTA/SM
-        case 4: return launch_cfg<8, 2, 4, 2, 224>(h, a);   // 104 KB, 2 CTA/SM
-        case 5: return launch_cfg<8, 8, 2, 2, 224>(h, a);   // 160 KB, 1 CTA/SM
-        case 6: return launch_cfg<8, 2, 2, 1, 168>(h, a);   //  64 KB, 3 CTA/SM, tighter registers
-        default: return launch_cfg<8, 2, 2, 1, 224>(h, a);  //  64 KB, 3 CTA/SM
-      }
-    case 9: return launch_cfg<9, 1, 3, 1, 224>(h, a);
-    case 10: return launch_cfg<10, 1, 3, 1, 224>(h, a);
     default: return fail(B200_ERR_ARG, "lx=%d not instantiated (4..10)", h->lx);
   }
 }
@@ -581,6 +542,21 @@ int gs_launch(Handle* h, double* f0, double* f1, double* f2, int nf) {
   else if (h->gs_un == 4) gs_op_kernel<3, 4, 2><<<grid_for(h->nclass, threads, h->num_sm, 2), threads, 0, h->stream>>>(
       f0, f1, f2, h->gs_off, h->gs_dof, h->nclass);
   else gs_op_kernel<3, 1, 3><<<grid3, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+// rank-local pass of the fused step: all classes (minus the shared-node classes of a multi-GPU run), or, after
+// an element kernel with the x stage, the classes that kernel left over
+int gs_step_pass(Handle* h, double* f0, double* f1, double* f2, bool xs) {
+  const int nc = xs ? h->xs_nclass : h->nclass;
+  if (nc == 0) return B200_OK;
+  const int threads = 256, grid = grid_for(nc, threads, h->num_sm, 3);
+  if (xs)
+    gs_op_kernel<3, 1, 3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->xs_off, h->xs_dof, nc, h->xs_skip);
+  else
+    gs_op_kernel<3, 1, 3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, nc, h->gs_skip);
   LAUNCHED();
   CK(cudaGetLastError());
   return B200_OK;
@@ -721,6 +697,103 @@ int build_gs_schedule(Handle* h, const int* list, int nlist) {
   return B200_OK;
 }
 
+
+// multi-GPU shared-node state (b200_gs_init_shared); it refers to the class list of the last b200_gs_init
+void free_shared(Handle* h) {
+  cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
+  cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->gs_skip);
+  cudaFree(h->gs_shared_cls);
+  h->d_send_dof = h->d_shared_dof = h->d_s_class = h->d_c_off = h->d_c_src = nullptr;
+  h->d_send = h->d_recv = nullptr; h->gs_skip = nullptr; h->gs_shared_cls = nullptr;
+  h->n_shared_cls = 0; h->nsend = 0; h->nshared = 0; h->nneigh = 0;
+  h->neigh_rank.clear(); h->neigh_off.clear();
+}
+
+void free_xstage(Handle* h) {
+  cudaFree(h->xs_link); cudaFree(h->xs_off); cudaFree(h->xs_dof); cudaFree(h->xs_skip);
+  h->xs_link = nullptr; h->xs_off = h->xs_dof = nullptr; h->xs_skip = nullptr;
+  h->xs_valid = false; h->xs_nclass = 0; h->xs_nslots = 0; h->xs_nlinked = 0; h->xs_nmember = 0;
+}
+
+// frees device temporaries on every exit path of a set-up routine
+struct DevTemps {
+  std::vector<void*> ptrs;
+  ~DevTemps() { for (void* q : ptrs) cudaFree(q); }
+  template <typename T>
+  int alloc(T** q, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(q), std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "cudaMalloc of a set-up buffer failed: %s", cudaGetErrorString(e));
+    ptrs.push_back(*q);
+    return B200_OK;
+  }
+};
+
+// x stage of the lx = 8 element kernel: link flags per element + CSR lists of the classes left to the
+// gather-scatter pass (gs_kernels.cuh "x stage").  Needs gs_init (and gs_init_shared, if any) done.
+int build_xstage(Handle* h) {
+  free_xstage(h);
+  if (!h->have_gs || h->lx != 8 || h->nelv == 0) return B200_OK;
+  cudaStream_t st = h->stream;
+  const int nc = h->nclass, ne = h->nelv, threads = 256;
+  const int nslots = std::min((ne + XS_NE - 1) / XS_NE, h->num_sm) * XS_NE;
+  if (int r = dmalloc(&h->xs_link, (size_t)ne)) return r;
+  CK(cudaMemsetAsync(h->xs_link, 0, (size_t)ne, st));
+  h->xs_nslots = nslots;
+  if (nc == 0) {
+    if (int r = dmalloc(&h->xs_off, 1)) return r;
+    if (int r = dmalloc(&h->xs_dof, 1)) return r;
+    CK(cudaMemsetAsync(h->xs_off, 0, sizeof(int), st));
+    h->xs_valid = true;
+    return B200_OK;
+  }
+  DevTemps T;
+  int *d_cnt = nullptr, *d_keep = nullptr, *d_mem = nullptr, *d_newidx = nullptr, *d_newoff = nullptr;
+  if (int r = T.alloc(&d_cnt, (size_t)ne)) return r;
+  if (int r = T.alloc(&d_keep, (size_t)nc)) return r;
+  if (int r = T.alloc(&d_mem, (size_t)nc)) return r;
+  if (int r = T.alloc(&d_newidx, (size_t)nc)) return r;
+  if (int r = T.alloc(&d_newoff, (size_t)nc)) return r;
+  CK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (size_t)ne, st));
+  const int gc = grid_for(nc, threads, h->num_sm, 8);
+  if (!h->xs_nolink) {
+    xs_candidate_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, h->xs_shift, d_cnt);
+    LAUNCHED();
+  }
+  xs_link_kernel<<<grid_for(ne, threads, h->num_sm, 8), threads, 0, st>>>(d_cnt, ne, h->xs_link);
+  LAUNCHED();
+  xs_keep_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, h->xs_shift, h->xs_link, d_keep, d_mem);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  void* d_tmp = nullptr;
+  size_t tb1 = 0, tb2 = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb1, d_keep, d_newidx, nc, st));
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_mem, d_newoff, nc, st));
+  if (int r = T.alloc(reinterpret_cast<unsigned char**>(&d_tmp), std::max(tb1, tb2))) return r;
+  CK(cub::DeviceScan::ExclusiveSum(d_tmp, tb1, d_keep, d_newidx, nc, st));
+  CK(cub::DeviceScan::ExclusiveSum(d_tmp, tb2, d_mem, d_newoff, nc, st));
+  int last[4] = {};
+  CK(cudaMemcpyAsync(&last[0], d_newidx + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&last[1], d_keep + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&last[2], d_newoff + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&last[3], d_mem + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int nkeep = last[0] + last[1], nmem = last[2] + last[3];
+  if (int r = dmalloc(&h->xs_off, (size_t)nkeep + 1)) return r;
+  if (int r = dmalloc(&h->xs_dof, (size_t)nmem)) return r;
+  if (h->gs_skip) if (int r = dmalloc(&h->xs_skip, (size_t)nkeep)) return r;
+  xs_compact_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, d_keep, d_newidx, d_newoff, h->gs_skip,
+                                            h->xs_off, h->xs_dof, h->xs_skip);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->xs_off + nkeep, &nmem, sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  h->xs_nclass = nkeep;
+  h->xs_nmember = nmem;
+  h->xs_nlinked = ((int64_t)nc - nkeep) / 36;
+  h->xs_valid = true;
+  return B200_OK;
+}
+
 // separate gather-scatter pass over the packed lists of the schedule (3 fields); entries [lo[b], hi[b]) of
 // list b = 0..3 (pairs, quads, octs, hexes)
 int gs_packed_range(Handle* h, double* f0, double* f1, double* f2, const int lo[4], const int hi[4]) {
@@ -790,6 +863,7 @@ LaunchArgs make_args(const void* vx, const void* vy, const void* vz, const void*
   a.elem_begin = 0;
   a.no_dealias = false;
   a.gs_in_kernel = false;
+  a.xstage = false;
   return a;
 }
 
@@ -831,7 +905,20 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
     delete h;
     return fail(B200_ERR_ARG, "create: n=%lld exceeds int32 dof indexing", nn);
   }
-  h->device = device ? *device : 0;
+  // *device < 0 (or NULL): the calling thread's current CUDA device -- what a Neko rank has selected in
+  // device_init; the handle then never moves the thread to another device
+  h->device = device ? *device : -1;
+  if (h->device < 0) {
+    if (cudaGetDevice(&h->device) != cudaSuccess) {
+      delete h;
+      return fail(B200_ERR_CUDA, "create: cudaGetDevice failed");
+    }
+  }
+  if (h->device >= ndev) {
+    const int d = h->device;
+    delete h;
+    return fail(B200_ERR_ARG, "create: device %d of %d", d, ndev);
+  }
   CK(cudaSetDevice(h->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, h->device));
@@ -855,6 +942,18 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   if (g) h->gs_lag = std::max(1, atoi(g));
   g = getenv("B200_GS_L2HINT");
   if (g) h->gs_l2hint = atoi(g) != 0;
+  g = getenv("B200_XSTAGE");
+  if (g) h->xs_enable = atoi(g) != 0;
+  g = getenv("B200_XS_RUN");       // run length (rounded down to a power of two; 0: one contiguous run per slot)
+  if (g) {
+    const int r = atoi(g);
+    h->xs_shift = 30;
+    if (r > 0) { h->xs_shift = 0; while ((2 << h->xs_shift) <= r && h->xs_shift < 30) h->xs_shift++; }
+  }
+  g = getenv("B200_XS_VARIANT");
+  if (g) h->xs_variant = atoi(g) == 1 ? 1 : 2;
+  g = getenv("B200_XS_NOLINK");
+  if (g) h->xs_nolink = atoi(g) != 0;
   *handle = h;
   return B200_OK;
 }
@@ -864,12 +963,11 @@ int b200_adjrhs_free(void** handle) {
   Handle* h = H(*handle);
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep); cudaFree(h->gs_skip);
-  cudaFree(h->gs_shared_cls); cudaFree(h->geom_pack); cudaFree(h->G_fine);
-  free_schedule(h); cudaFree(h->d_order); cudaFree(h->work6); cudaFree(h->d_partial);
-  cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
-  cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_bnd_elem);
-  cudaFree(h->d_int_elem);
+  cudaFree(h->gs_off); cudaFree(h->gs_dof); cudaFree(h->gs_rep);
+  free_shared(h);
+  cudaFree(h->geom_pack); cudaFree(h->G_fine);
+  free_schedule(h); free_xstage(h); cudaFree(h->d_order); cudaFree(h->work6); cudaFree(h->d_partial);
+  cudaFree(h->d_bnd_elem); cudaFree(h->d_int_elem);
   for (double* s : h->stage) cudaFree(s);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->pev) if (e) cudaEventDestroy(e);
@@ -968,6 +1066,7 @@ int b200_adjrhs_compute(void* handle, const void* vx, const void* vy, const void
   if (int r = check_fields({vx, vy, vz, vxb, vyb, vzb, rho, chi_in, fsx, fsy, fsz, fx, fy, fz, sens, chi_out}))
     return r;
   CK(cudaSetDevice(h->device));
+  NvtxRange nvtx("Fluid: adjoint RHS (b200_adjrhs_compute)");
   LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, rho, chi_in, fsx, fsy, fsz, fx, fy, fz, sens,
                            chi_out, h->nelv);
   if (int r = launch_fused(h, a)) return r;
@@ -989,6 +1088,7 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
   LaunchArgs a = make_args(vx, vy, vz, vxb, vyb, vzb, rho, chi_in, fsx, fsy, fsz, fx, fy, fz, sens,
                            chi_out, h->nelv);
   double *f0 = a.f[0], *f1 = a.f[1], *f2 = a.f[2];
+  NvtxRange nvtx_step("Fluid: adjoint RHS + Velocity residual gs_op (b200_adjrhs_step)");
   if (int r = time_mark(h)) return r;
   // Multi-GPU, default: ONE launch over all elements, then the classes holding shared nodes are summed and
   // packed, and the NCCL exchange runs on the communication stream WHILE the remaining (rank-local) classes
@@ -998,9 +1098,20 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
   // delays the NCCL kernel or starts some of its CTAs late behind it (static element partition), and the
   // element-list variant of the kernel is ~12 % slower than the contiguous one.
   const bool mgpu = h->comm && h->nshared > 0 && h->n_shared_cls >= 0 && h->gs_skip;
+  // x stage (lx = 8 default kernel, mesh order, CSR pass): the element kernel sums the i-face pair classes of
+  // consecutive elements itself and the pass runs over the remaining classes only.  The masked lube term is
+  // added to single nodes after the element kernel, so it needs the un-summed values.
+  const bool masked_lube = a.sources && h->if_lube && h->lube_mask_size > 0;
+  bool xs = h->xs_enable && uses_v3(h) && h->gs_mode == 0 && !h->d_order && !masked_lube &&
+            !(mgpu && h->overlap_elem) && !(h->comm && h->nshared > 0 && !mgpu);
+  if (xs && !h->xs_valid) {
+    if (int r = build_xstage(h)) return r;
+    xs = h->xs_valid;
+  }
   if (mgpu && !h->overlap_elem) {
     if (int r = phase_mark(h, 0)) return r;
     a.elem_list = h->d_order;
+    a.xstage = xs;
     if (int r = launch_fused(h, a)) return r;
     if (int r = masked_lube_post(h, a)) return r;
     if (int r = phase_mark(h, 1)) return r;
@@ -1015,13 +1126,7 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     if (int r = phase_mark(h, 2)) return r;
     if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
     if (int r = phase_mark(h, 3)) return r;
-    if (h->nclass > 0) {
-      const int threads = 256, grid = grid_for(h->nclass, threads, h->num_sm, 3);
-      gs_op_kernel<3, 1, 3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->nclass,
-                                                              h->gs_skip);
-      LAUNCHED();
-      CK(cudaGetLastError());
-    }
+    if (int r = gs_step_pass(h, f0, f1, f2, xs)) return r;
     if (int r = phase_mark(h, 4)) return r;
     if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
     if (int r = phase_mark(h, 5)) return r;
@@ -1030,7 +1135,6 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
   const bool split = mgpu && h->nbnd > 0;
   // direct-stiffness summation inside the element kernel (v3, lx = 8) while f is still in L2; the masked
   // lube term is applied by a separate kernel after the element kernel, so it keeps the separate gs pass
-  const bool masked_lube = a.sources && h->if_lube && h->lube_mask_size > 0;
   // gs_mode 2: summation inside the v3 element kernel; 1: separate pass over the packed class lists of the
   // schedule; 0: the CSR kernels.  Without a boundary/interior split a communicator needs the CSR pass
   // (it sums the shared classes too, before the exchange).
@@ -1087,6 +1191,7 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     if (int r = phase_mark(h, 6)) return r;
   } else {
     a.elem_list = h->d_order; a.gs_in_kernel = fuse_gs;
+    a.xstage = xs && mode == 0;
     if (int r = launch_fused(h, a)) return r;
     if (int r = masked_lube_post(h, a)) return r;
     if (int r = time_mark(h)) return r;
@@ -1095,6 +1200,8 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     } else if (mode == 1) {
       if (int r = gs_packed(h, f0, f1, f2)) return r;
       if (int r = gs_leftover(h, f0, f1, f2)) return r;
+    } else if (a.xstage) {
+      if (int r = gs_step_pass(h, f0, f1, f2, true)) return r;
     } else {
       if (int r = gs_launch(h, f0, f1, f2, 3)) return r;
       if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
@@ -1143,6 +1250,24 @@ int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, in
   Handle* h = H(handle);
   if (fused) *fused = (h->sched_valid && h->gs_mode == 2) ? 1 : 0;
   if (classes_in_kernel) *classes_in_kernel = h->sched_valid ? h->sched_nfused : 0;
+  if (classes_total) *classes_total = h->nclass;
+  return B200_OK;
+}
+
+int b200_adjrhs_set_xstage(void* handle, const int* flag) {
+  if (!handle || !flag) return fail(B200_ERR_ARG, "set_xstage: null argument");
+  H(handle)->xs_enable = (*flag != 0);
+  return B200_OK;
+}
+
+int b200_adjrhs_xstage_info(void* handle, int* active, int64_t* linked_elements, int64_t* classes_left,
+                            int64_t* classes_total) {
+  if (!handle) return fail(B200_ERR_ARG, "null handle");
+  Handle* h = H(handle);
+  const bool on = h->xs_enable && h->xs_valid;
+  if (active) *active = on ? 1 : 0;
+  if (linked_elements) *linked_elements = on ? h->xs_nlinked : 0;
+  if (classes_left) *classes_left = on ? h->xs_nclass : h->nclass;
   if (classes_total) *classes_total = h->nclass;
   return B200_OK;
 }
@@ -1340,17 +1465,23 @@ int b200_sensitivity(void* sens, const void* u, const void* v, const void* w, co
 
 int b200_steady_field_update(double* result, const void* x, void* x_old, const int* n, void* stream) {
   if (!result || !x || !x_old || !n) return fail(B200_ERR_ARG, "steady_field_update: null argument");
-  double* d_res = nullptr;
-  CK(cudaMalloc(&d_res, sizeof(double)));
-  CK(cudaMemsetAsync(d_res, 0, sizeof(double), (cudaStream_t)stream));
-  const int threads = 256;
-  steady_update_kernel<<<grid_for(*n, threads, dev_sm_count(), 4), threads, 0, (cudaStream_t)stream>>>(
-      d_res, (const double*)x, (double*)x_old, *n);
+  if (*n < 0) return fail(B200_ERR_ARG, "steady_field_update: n=%d", *n);
+  // per-device scratch (partials + result), allocated once: the call runs every time step
+  static double* scratch[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(B200_ERR_ARG, "steady_field_update: device index %d", dev);
+  if (!scratch[dev]) CK(cudaMalloc(&scratch[dev], sizeof(double) * (STEADY_BLOCKS + 1)));
+  double* d_part = scratch[dev];
+  double* d_res = d_part + STEADY_BLOCKS;
+  cudaStream_t st = (cudaStream_t)stream;
+  steady_update_kernel<<<STEADY_BLOCKS, 256, 0, st>>>(d_part, (const double*)x, (double*)x_old, (int64_t)*n);
+  LAUNCHED();
+  steady_reduce_kernel<<<1, 256, 0, st>>>(d_part, d_res);
   LAUNCHED();
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(result, d_res, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  CK(cudaStreamSynchronize((cudaStream_t)stream));
-  CK(cudaFree(d_res));
+  CK(cudaMemcpyAsync(result, d_res, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return B200_OK;
 }
 
@@ -1525,6 +1656,7 @@ int b200_pde_filter_apply(void* handle, void* x_out, const void* x_in, const voi
   if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
   if (!h->have_gs) return fail(B200_ERR_STATE, "pde_filter_apply: b200_gs_init not called");
   CK(cudaSetDevice(h->device));
+  NvtxRange nvtx("PDE filter solve (b200_pde_filter_apply)");
   const int64_t n = h->n;
   if (!h->work6 && n > 0) if (int r = dmalloc(&h->work6, 6 * (size_t)n)) return r;
   double *rr = h->work6, *pp = rr + n, *zz = pp + n, *ww = zz + n, *dinv = ww + n;
@@ -1670,6 +1802,8 @@ int b200_gs_init(void* handle, const int64_t* key, const int* on_device) {
   h->gs_off = h->gs_dof = h->gs_rep = nullptr;
   h->have_gs = false;
   free_schedule(h);
+  free_xstage(h);
+  free_shared(h);      // the shared-node lists index the old class list: b200_gs_init_shared must be called again
   if (n == 0) { h->nclass = 0; h->nmember = 0; h->have_gs = true; return B200_OK; }
 
   int64_t *d_key_in = nullptr, *d_key = nullptr, *d_comp = nullptr, *d_comp2 = nullptr;
@@ -1805,6 +1939,7 @@ int b200_gs_op(void* handle, void* f) {
   if (!handle || !f) return fail(B200_ERR_ARG, "gs_op: null argument");
   Handle* h = H(handle);
   CK(cudaSetDevice(h->device));
+  NvtxRange nvtx("Velocity residual: gs_op (b200_gs_op)");
   double* f0 = (double*)f;
   if (int r = gs_launch(h, f0, f0, f0, 1)) return r;
   if (int r = gs_exchange(h, f0, f0, f0, 1)) return r;
@@ -1816,6 +1951,7 @@ int b200_gs_op3(void* handle, void* fx, void* fy, void* fz) {
   Handle* h = H(handle);
   CK(cudaSetDevice(h->device));
   double *f0 = (double*)fx, *f1 = (double*)fy, *f2 = (double*)fz;
+  NvtxRange nvtx("Velocity residual: gs_op x3 (b200_gs_op3)");
   if (int r = gs_launch(h, f0, f1, f2, 3)) return r;
   if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
   return gs_finish_exchange(h, f0, f1, f2, 3);
@@ -1852,15 +1988,11 @@ int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof,
   if (!h->have_gs) return fail(B200_ERR_STATE, "gs_init_shared: call b200_gs_init first");
   CK(cudaSetDevice(h->device));
   const int ns = *nshared, nn = *nneigh;
-  h->nshared = ns; h->nneigh = nn;
   free_schedule(h);
-  cudaFree(h->d_send_dof); cudaFree(h->d_shared_dof); cudaFree(h->d_s_class); cudaFree(h->d_c_off);
-  cudaFree(h->d_c_src); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->gs_skip);
-  cudaFree(h->gs_shared_cls);
-  h->d_send_dof = h->d_shared_dof = h->d_s_class = h->d_c_off = h->d_c_src = nullptr;
-  h->d_send = h->d_recv = nullptr; h->gs_skip = nullptr; h->gs_shared_cls = nullptr;
-  h->n_shared_cls = 0; h->nsend = 0;
-  if (ns == 0 || nn == 0) { h->nshared = 0; return B200_OK; }
+  free_xstage(h);
+  free_shared(h);
+  h->nshared = ns; h->nneigh = nn;
+  if (ns == 0 || nn == 0) { h->nshared = 0; h->nneigh = 0; return B200_OK; }
   if (!shared_dof || !neigh_rank || !neigh_off || !neigh_idx) return fail(B200_ERR_ARG, "gs_init_shared: null list");
   // neighbours in ascending rank order so that every rank sums contributions in the same order
   std::vector<int> order(nn);
@@ -1921,6 +2053,150 @@ int b200_gs_init_shared(void* handle, const int* nshared, const int* shared_dof,
   if (int r = dmalloc(&h->gs_shared_cls, cls.size())) return r;
   if (!cls.empty())
     CK(cudaMemcpy(h->gs_shared_cls, cls.data(), sizeof(int) * cls.size(), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+// Shared-node discovery on the device + NCCL: what Neko's gs_t%init does from the dofmap
+// (adjoint/adjoint_scheme.f90:339-343).  See include/neko_top_b200.h.
+int b200_gs_init_shared_from_keys(void* handle, const int64_t* key, const int* on_device,
+                                  const unsigned char* cand, int* nshared_out, int* nneigh_out) {
+  if (!handle || !key) return fail(B200_ERR_ARG, "gs_init_shared_from_keys: null argument");
+  Handle* h = H(handle);
+  if (!h->have_gs) return fail(B200_ERR_STATE, "gs_init_shared_from_keys: call b200_gs_init first");
+  if (!h->comm) return fail(B200_ERR_STATE, "gs_init_shared_from_keys: call b200_comm_init first");
+  if (h->nranks > 64) return fail(B200_ERR_ARG, "gs_init_shared_from_keys: at most 64 ranks");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int64_t n = h->n;
+  const int threads = 256, nr = h->nranks;
+  const bool dev_in = on_device && *on_device;
+  DevTemps T;
+  const int64_t* d_key = key;
+  unsigned char* d_flag = nullptr;
+  if (!dev_in) {
+    int64_t* tmp = nullptr;
+    if (int r = T.alloc(&tmp, (size_t)n)) return r;
+    CK(cudaMemcpyAsync(tmp, key, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    d_key = tmp;
+  }
+  if (int r = T.alloc(&d_flag, (size_t)n)) return r;
+  if (cand) {
+    CK(cudaMemcpyAsync(d_flag, cand, (size_t)n, dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  } else if (n > 0) {
+    shk_surface_kernel<<<grid_for(n, threads, h->num_sm, 8), threads, 0, st>>>(d_flag, n, h->lx);
+    LAUNCHED();
+  }
+  // 1. candidate dofs, their keys, stable sort by key -> unique keys with the smallest dof of each
+  int *d_idx = nullptr, *d_idx2 = nullptr;
+  int64_t *d_cnt1 = nullptr, *d_k = nullptr, *d_k2 = nullptr;
+  void* d_tmp = nullptr;
+  size_t tb = 0;
+  if (int r = T.alloc(&d_idx, (size_t)n)) return r;
+  if (int r = T.alloc(&d_cnt1, 2 + (size_t)nr)) return r;
+  thrust::counting_iterator<int> cnt0(0);
+  CK(cub::DeviceSelect::Flagged(nullptr, tb, cnt0, d_flag, d_idx, d_cnt1, n, st));
+  if (int r = T.alloc(reinterpret_cast<unsigned char**>(&d_tmp), tb)) return r;
+  CK(cub::DeviceSelect::Flagged(d_tmp, tb, cnt0, d_flag, d_idx, d_cnt1, n, st));
+  int64_t ncand = 0;
+  CK(cudaMemcpyAsync(&ncand, d_cnt1, sizeof ncand, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int m = (int)ncand;
+  if (int r = T.alloc(&d_k, (size_t)m)) return r;
+  if (int r = T.alloc(&d_k2, (size_t)m)) return r;
+  if (int r = T.alloc(&d_idx2, (size_t)m)) return r;
+  unsigned char* d_head = nullptr;
+  int64_t* d_uk = nullptr;
+  int* d_udof = nullptr;
+  if (int r = T.alloc(&d_head, (size_t)m)) return r;
+  if (int r = T.alloc(&d_uk, (size_t)m)) return r;
+  if (int r = T.alloc(&d_udof, (size_t)m)) return r;
+  int64_t nuk64 = 0;
+  if (m > 0) {
+    shk_gather_kernel<<<grid_for(m, threads, h->num_sm, 8), threads, 0, st>>>(d_key, d_idx, m, d_k);
+    LAUNCHED();
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_k, d_k2, d_idx, d_idx2, m, 0, 64, st));
+    void* d_tmp2 = nullptr;
+    if (int r = T.alloc(reinterpret_cast<unsigned char**>(&d_tmp2), tb)) return r;
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp2, tb, d_k, d_k2, d_idx, d_idx2, m, 0, 64, st));
+    shk_head_kernel<<<grid_for(m, threads, h->num_sm, 8), threads, 0, st>>>(d_k2, m, d_head);
+    LAUNCHED();
+    void* d_tmp3 = nullptr;
+    CK(cub::DeviceSelect::Flagged(nullptr, tb, d_k2, d_head, d_uk, d_cnt1, m, st));
+    if (int r = T.alloc(reinterpret_cast<unsigned char**>(&d_tmp3), tb)) return r;
+    CK(cub::DeviceSelect::Flagged(d_tmp3, tb, d_k2, d_head, d_uk, d_cnt1, m, st));
+    CK(cub::DeviceSelect::Flagged(d_tmp3, tb, d_idx2, d_head, d_udof, d_cnt1, m, st));
+    CK(cudaMemcpyAsync(&nuk64, d_cnt1, sizeof nuk64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  const int nuk = (int)nuk64;
+  // 2. all-gather the counts, then the padded key lists
+  int64_t* d_cnts = d_cnt1 + 2;
+  CK(cudaMemcpyAsync(d_cnt1, &nuk64, sizeof nuk64, cudaMemcpyHostToDevice, st));
+  NK(ncclAllGather(d_cnt1, d_cnts, 1, ncclInt64, h->comm, st));
+  std::vector<int64_t> cnts(nr);
+  CK(cudaMemcpyAsync(cnts.data(), d_cnts, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int64_t mpad = 1;
+  for (int r = 0; r < nr; r++) mpad = std::max(mpad, cnts[r]);
+  int64_t *d_pad = nullptr, *d_all = nullptr;
+  if (int r = T.alloc(&d_pad, (size_t)mpad)) return r;
+  if (int r = T.alloc(&d_all, (size_t)mpad * nr)) return r;
+  CK(cudaMemsetAsync(d_pad, 0xff, sizeof(int64_t) * (size_t)mpad, st));
+  if (nuk > 0) CK(cudaMemcpyAsync(d_pad, d_uk, sizeof(int64_t) * (size_t)nuk, cudaMemcpyDeviceToDevice, st));
+  NK(ncclAllGather(d_pad, d_all, (size_t)mpad, ncclInt64, h->comm, st));
+  // 3. which of my unique candidate keys live on which other rank
+  unsigned long long* d_hit = nullptr;
+  if (int r = T.alloc(&d_hit, (size_t)nuk)) return r;
+  if (nuk > 0) {
+    shk_hit_kernel<<<grid_for(nuk, threads, h->num_sm, 8), threads, 0, st>>>(d_uk, nuk, d_all, mpad, d_cnts, nr,
+                                                                            h->rank, d_hit);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
+  std::vector<unsigned long long> hit(nuk);
+  std::vector<int> udof(nuk);
+  std::vector<int64_t> uk(nuk);
+  std::vector<int64_t> ks(m);
+  std::vector<int> kd(m);
+  if (nuk > 0) {
+    CK(cudaMemcpyAsync(hit.data(), d_hit, sizeof(unsigned long long) * nuk, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(udof.data(), d_udof, sizeof(int) * nuk, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(uk.data(), d_uk, sizeof(int64_t) * nuk, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ks.data(), d_k2, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(kd.data(), d_idx2, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  // 4. host: compact numbering of the shared nodes (ascending key), per-neighbour lists in ascending key order
+  //    (both sides of a pair build the same order without a handshake), elements owning a shared node
+  std::vector<int> sidx(nuk, -1), shared_dof;
+  for (int i = 0; i < nuk; i++)
+    if (hit[i]) { sidx[i] = (int)shared_dof.size(); shared_dof.push_back(udof[i]); }
+  std::vector<int> neigh_rank, neigh_off(1, 0), neigh_idx;
+  for (int r = 0; r < nr; r++) {
+    size_t before = neigh_idx.size();
+    for (int i = 0; i < nuk; i++)
+      if (hit[i] >> r & 1ull) neigh_idx.push_back(sidx[i]);
+    if (neigh_idx.size() > before) { neigh_rank.push_back(r); neigh_off.push_back((int)neigh_idx.size()); }
+  }
+  const int N3 = h->lx * h->lx * h->lx;
+  std::vector<char> isb(h->nelv, 0);
+  {
+    int u = -1;                                   // walk the sorted candidate (key, dof) pairs and the unique keys together
+    for (int i = 0; i < m; i++) {
+      if (i == 0 || ks[i] != ks[i - 1]) u++;
+      if (hit[u]) isb[kd[i] / N3] = 1;
+    }
+  }
+  std::vector<int> bnd;
+  for (int e = 0; e < h->nelv; e++) if (isb[e]) bnd.push_back(e);
+  const int ns = (int)shared_dof.size(), nn = (int)neigh_rank.size();
+  if (int r = b200_gs_init_shared(handle, &ns, shared_dof.data(), &nn, neigh_rank.data(), neigh_off.data(),
+                                  neigh_idx.data()))
+    return r;
+  const int nb = (int)bnd.size();
+  if (int r = b200_adjrhs_set_boundary_elements(handle, &nb, bnd.data())) return r;
+  if (nshared_out) *nshared_out = ns;
+  if (nneigh_out) *nneigh_out = nn;
   return B200_OK;
 }
 

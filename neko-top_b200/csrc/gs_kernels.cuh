@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "adjrhs_kernel_v3.cuh"   // xs_map / xs_is_run_start: the element -> slot map of the x-stage kernels
+
 namespace b200 {
 
 __global__ void gs_iota_kernel(int* idx, int64_t n) {
@@ -364,6 +366,113 @@ __global__ void __launch_bounds__(256) gs_wide_kernel(double* __restrict__ f0, d
 #pragma unroll
     for (int m = 0; m < W; m++)
       if (d[m] >= 0) { f0[d[m]] = s0; f1[d[m]] = s1; f2[d[m]] = s2; }
+  }
+}
+
+// ---- x stage of the lx = 8 element kernel (adjrhs_kernel_v3.cuh, XS) -----------------------------------------
+// The element kernel sums, in registers, the 36 face-interior pair classes between element e-1 (i = 7) and
+// element e (i = 0) when the two faces are glued node by node with the same (j,k) orientation and both
+// elements are processed consecutively by one slot.  Set-up verifies this against the class lists:
+//   xs_candidate_kernel: a 2-member class {(e-1; 7,j,k), (e; 0,j,k)}, 1 <= j,k <= 6, e not the first element of a
+//                        slot's run, counts one for element e;
+//   xs_link_kernel:      xlink[e] = all 36 classes of the face were found;
+//   xs_keep_kernel:      a class stays in the gather-scatter pass unless it is such a pair of a linked element.
+// Runs: xs_map / xs_is_run_start in adjrhs_kernel_v3.cuh (windows of nslots runs of 2^shift elements + a balanced tail).
+// returns the later element of the pair if class c matches the pattern, else -1
+__device__ __forceinline__ int xs_pair_elem(const int* __restrict__ off, const int* __restrict__ dof, int c,
+                                            int nelem, int nslots, int shift) {
+  const int b = off[c];
+  if (off[c + 1] - b != 2) return -1;
+  const int d0 = dof[b], d1 = dof[b + 1];
+  const int e0 = d0 >> 9, e1 = d1 >> 9;
+  if (e1 != e0 + 1) return -1;
+  const int l0 = d0 & 511, l1 = d1 & 511;
+  if ((l0 & 7) != 7 || (l1 & 7) != 0 || (l0 >> 3) != (l1 >> 3)) return -1;
+  const int j = (l0 >> 3) & 7, k = l0 >> 6;
+  if (j < 1 || j > 6 || k < 1 || k > 6) return -1;
+  if (xs_is_run_start(e1, nelem, nslots, shift)) return -1;
+  return e1;
+}
+__global__ void xs_candidate_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass,
+                                    int nelem, int nslots, int shift, int* __restrict__ cnt) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
+    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots, shift);
+    if (e1 >= 0) atomicAdd(cnt + e1, 1);
+  }
+}
+__global__ void xs_link_kernel(const int* __restrict__ cnt, int nelem, unsigned char* __restrict__ xlink) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride) xlink[e] = (cnt[e] == 36) ? 1 : 0;
+}
+// keep[c] = 1 / members[c] = class size if the class stays in the pass, else 0 / 0
+__global__ void xs_keep_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass, int nelem,
+                               int nslots, int shift, const unsigned char* __restrict__ xlink, int* __restrict__ keep,
+                               int* __restrict__ members) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
+    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots, shift);
+    const bool k = !(e1 >= 0 && xlink[e1]);
+    keep[c] = k ? 1 : 0;
+    members[c] = k ? off[c + 1] - off[c] : 0;
+  }
+}
+// compacted CSR of the kept classes (+ their shared-node skip flags)
+__global__ void xs_compact_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass,
+                                  const int* __restrict__ keep, const int* __restrict__ newidx,
+                                  const int* __restrict__ newoff, const unsigned char* __restrict__ skip,
+                                  int* __restrict__ off2, int* __restrict__ dof2, unsigned char* __restrict__ skip2) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
+    if (!keep[c]) continue;
+    const int n = newidx[c], o = newoff[c], b = off[c], cnt = off[c + 1] - b;
+    off2[n] = o;
+    for (int m = 0; m < cnt; m++) dof2[o + m] = dof[b + m];
+    if (skip2) skip2[n] = skip ? skip[c] : 0;
+  }
+}
+
+// ---- shared-node discovery between ranks (b200_gs_init_shared_from_keys) ----------------------------------
+// candidate flags when the caller gives no mask: every dof on the surface of its element
+__global__ void shk_surface_kernel(unsigned char* __restrict__ flag, int64_t n, int lx) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int N = lx * lx * lx, L = lx - 1;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n; d += stride) {
+    const int l = (int)(d % N);
+    const int i = l % lx, j = (l / lx) % lx, k = l / (lx * lx);
+    flag[d] = (i == 0 || i == L || j == 0 || j == L || k == 0 || k == L) ? 1 : 0;
+  }
+}
+__global__ void shk_gather_kernel(const int64_t* __restrict__ key, const int* __restrict__ idx, int m,
+                                  int64_t* __restrict__ out) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) out[i] = key[idx[i]];
+}
+__global__ void shk_head_kernel(const int64_t* __restrict__ ks, int m, unsigned char* __restrict__ head) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+    head[i] = (i == 0 || ks[i] != ks[i - 1]) ? 1 : 0;
+}
+// hit[i] bit r: unique candidate key i of this rank is also a candidate key of rank r (binary search in the
+// all-gathered, sorted, padded key lists allk[r*mpad ..], cnt[r] valid entries)
+__global__ void shk_hit_kernel(const int64_t* __restrict__ uk, int nuk, const int64_t* __restrict__ allk,
+                               int64_t mpad, const int64_t* __restrict__ cnt, int nranks, int rank,
+                               unsigned long long* __restrict__ hit) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nuk; i += stride) {
+    const int64_t k = uk[i];
+    unsigned long long h = 0;
+    for (int r = 0; r < nranks; r++) {
+      if (r == rank) continue;
+      const int64_t* a = allk + (size_t)r * mpad;
+      int64_t lo = 0, hi = cnt[r];
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < k) lo = mid + 1; else hi = mid;
+      }
+      if (lo < cnt[r] && a[lo] == k) h |= 1ull << r;
+    }
+    hit[i] = h;
   }
 }
 

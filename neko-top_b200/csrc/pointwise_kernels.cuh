@@ -147,10 +147,13 @@ __global__ void geom_pack_kernel(GeomPtrs g, double* __restrict__ out, int plane
   }
 }
 
-// steady_simcomp.f90:158-176: d = old - new; acc += d*d; old = new.  One double atomic per CTA.
-__global__ void steady_update_kernel(double* __restrict__ result, const double* __restrict__ x,
-                                     double* __restrict__ x_old, int64_t n) {
-  __shared__ double red[32];
+// steady_simcomp.f90:158-176 for one field: d = old - new; acc += d*d; old = new.  Deterministic: every CTA of a
+// FIXED grid (STEADY_BLOCKS, independent of n and of the device) writes one partial sum, steady_reduce_kernel adds
+// the partials in a fixed tree -- the same bits on every run (field_glsc2 on one rank is a plain ordered sum too).
+constexpr int STEADY_BLOCKS = 1024;
+__global__ void __launch_bounds__(256) steady_update_kernel(double* __restrict__ partial, const double* __restrict__ x,
+                                                            double* __restrict__ x_old, int64_t n) {
+  __shared__ double red[8];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -162,11 +165,24 @@ __global__ void steady_update_kernel(double* __restrict__ result, const double* 
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    acc = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (threadIdx.x == 0) atomicAdd(result, acc);
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    partial[blockIdx.x] = t;
   }
+}
+// one CTA of 256 threads: result = sum of the STEADY_BLOCKS partials (fixed order)
+__global__ void __launch_bounds__(256) steady_reduce_kernel(const double* __restrict__ partial, double* __restrict__ result) {
+  __shared__ double red[256];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < STEADY_BLOCKS; i += 256) t += partial[i];
+  red[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *result = red[0];
 }
 
 // ---- explicit time scheme around the RHS (adjoint_pnpn.f90:665-666,688-696; Neko rhs_maker types) --------

@@ -70,15 +70,16 @@ contains
     class(adv_lin_dealias_b200_t), intent(inout) :: this
     integer, intent(in) :: lxd
     type(coef_t), intent(inout), target :: coef
-    integer(c_int) :: ierr, lxd_c
+    integer(c_int) :: lxd_c
 
     call this%adv_lin_b200_t%init(coef)
     call this%Xh_GL%init(GL, lxd, lxd, lxd)
     call this%GLL_to_GL%init(this%Xh_GL, coef%Xh)
     lxd_c = lxd
     ! GLL_to_GL%Xh_to_Yh is the (lxd x lx) interpolation matrix J(a,l)
-    ierr = b200_adv_dealias_init(this%handle, lxd_c, &
-         this%GLL_to_GL%Xh_to_Yh, this%Xh_GL%dx, this%Xh_GL%wx)
+    call b200_check(b200_adv_dealias_init(this%handle, lxd_c, &
+         this%GLL_to_GL%Xh_to_Yh, this%Xh_GL%dx, this%Xh_GL%wx), &
+         'b200_adv_dealias_init')
   end subroutine init_dealias_b200
 
   !> Same argument list as `compute_adjoint_advection_dealias`; `f` in/out.
@@ -91,10 +92,10 @@ contains
     type(field_t), intent(inout) :: vxb, vyb, vzb
     type(field_t), intent(inout) :: fx, fy, fz
     integer, intent(in) :: n
-    integer(c_int) :: ierr
 
-    ierr = b200_adv_adjoint_dealias_compute(this%handle, vx%x_d, vy%x_d, &
-         vz%x_d, vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d)
+    call b200_check(b200_adv_adjoint_dealias_compute(this%handle, vx%x_d, vy%x_d, &
+         vz%x_d, vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d), &
+         'b200_adv_adjoint_dealias_compute')
   end subroutine adjoint_advection_dealias_b200
 
   !> Same argument list as `compute_linear_advection_dealias`; `f` in/out.
@@ -107,10 +108,10 @@ contains
     type(field_t), intent(inout) :: vxb, vyb, vzb
     type(field_t), intent(inout) :: fx, fy, fz
     integer, intent(in) :: n
-    integer(c_int) :: ierr
 
-    ierr = b200_adv_linear_dealias_compute(this%handle, vx%x_d, vy%x_d, &
-         vz%x_d, vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d)
+    call b200_check(b200_adv_linear_dealias_compute(this%handle, vx%x_d, vy%x_d, &
+         vz%x_d, vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d), &
+         'b200_adv_linear_dealias_compute')
   end subroutine linear_advection_dealias_b200
 
   !> Constructor; same argument as `init_no_dealias`.
@@ -118,7 +119,7 @@ contains
   subroutine init_b200(this, coef)
     class(adv_lin_b200_t), intent(inout) :: this
     type(coef_t), intent(in) :: coef
-    integer(c_int) :: ierr, lx, nelv, dev
+    integer(c_int) :: lx, nelv, dev
 
     if (NEKO_BCKND_DEVICE .ne. 1) then
        call neko_error('adv_lin_b200_t needs the CUDA device backend')
@@ -126,24 +127,28 @@ contains
     call this%free()
     lx = coef%Xh%lx
     nelv = coef%msh%nelv
-    dev = 0
-    ierr = b200_adjrhs_create(this%handle, lx, nelv, dev)
-    ierr = b200_adjrhs_set_stream(this%handle, glb_cmd_queue)
-    ierr = b200_adjrhs_set_space(this%handle, coef%Xh%dx, coef%Xh%wx)
-    ierr = b200_adjrhs_set_geometry(this%handle, &
+    dev = -1 ! the CUDA device Neko selected for this rank (device_init)
+    call b200_check(b200_adjrhs_create(this%handle, lx, nelv, dev), &
+         'b200_adjrhs_create')
+    call b200_check(b200_adjrhs_set_stream(this%handle, glb_cmd_queue), &
+         'b200_adjrhs_set_stream')
+    call b200_check(b200_adjrhs_set_space(this%handle, coef%Xh%dx, coef%Xh%wx), &
+         'b200_adjrhs_set_space')
+    call b200_check(b200_adjrhs_set_geometry(this%handle, &
          coef%drdx_d, coef%dsdx_d, coef%dtdx_d, &
          coef%drdy_d, coef%dsdy_d, coef%dtdy_d, &
-         coef%drdz_d, coef%dsdz_d, coef%dtdz_d, coef%B_d)
+         coef%drdz_d, coef%dsdz_d, coef%dtdz_d, coef%B_d), &
+         'b200_adjrhs_set_geometry')
     this%jacinv_d = coef%jacinv_d
   end subroutine init_b200
 
   !> Destructor.
   subroutine free_b200(this)
     class(adv_lin_b200_t), intent(inout) :: this
-    integer(c_int) :: ierr
 
     if (c_associated(this%handle)) then
-       ierr = b200_adjrhs_free(this%handle)
+       call b200_check(b200_adjrhs_free(this%handle), &
+            'b200_adjrhs_free')
     end if
     this%handle = C_NULL_PTR
   end subroutine free_b200
@@ -159,10 +164,10 @@ contains
     type(field_t), intent(inout) :: vxb, vyb, vzb
     type(field_t), intent(inout) :: fx, fy, fz
     integer, intent(in) :: n
-    integer(c_int) :: ierr
 
-    ierr = b200_adv_adjoint_compute(this%handle, vx%x_d, vy%x_d, vz%x_d, &
-         vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d)
+    call b200_check(b200_adv_adjoint_compute(this%handle, vx%x_d, vy%x_d, vz%x_d, &
+         vxb%x_d, vyb%x_d, vzb%x_d, fx%x_d, fy%x_d, fz%x_d), &
+         'b200_adv_adjoint_compute')
   end subroutine adjoint_advection_b200
 
   !> f -= u'.grad U_b + U_b.grad u' (B-weighted); `f` in/out.
@@ -175,10 +180,10 @@ contains
     type(field_t), intent(inout) :: vxb, vyb, vzb
     type(field_t), intent(inout) :: fx, fy, fz
     integer, intent(in) :: n
-    integer(c_int) :: ierr
 
-    ierr = b200_adv_linear_compute(this%handle, vx%x_d, vy%x_d, vz%x_d, &
-         vxb%x_d, vyb%x_d, vzb%x_d, this%jacinv_d, fx%x_d, fy%x_d, fz%x_d)
+    call b200_check(b200_adv_linear_compute(this%handle, vx%x_d, vy%x_d, vz%x_d, &
+         vxb%x_d, vyb%x_d, vzb%x_d, this%jacinv_d, fx%x_d, fy%x_d, fz%x_d), &
+         'b200_adv_linear_compute')
   end subroutine linear_advection_b200
 
   !> The whole explicit RHS of the adjoint momentum equation in one kernel pass.
@@ -202,7 +207,6 @@ contains
     type(field_t), intent(inout), optional :: rho, chi, sens, fs_x, fs_y, fs_z
     logical, intent(in), optional :: with_gs
     type(c_ptr) :: rho_d, chi_d, sens_d, fsx_d, fsy_d, fsz_d
-    integer(c_int) :: ierr
     logical :: gs
 
     rho_d = C_NULL_PTR; chi_d = C_NULL_PTR; sens_d = C_NULL_PTR
@@ -217,13 +221,15 @@ contains
     if (present(with_gs)) gs = with_gs
 
     if (gs) then
-       ierr = b200_adjrhs_step(adv%handle, u%x_d, v%x_d, w%x_d, &
+       call b200_check(b200_adjrhs_step(adv%handle, u%x_d, v%x_d, w%x_d, &
             u_b%x_d, v_b%x_d, w_b%x_d, rho_d, chi_d, fsx_d, fsy_d, fsz_d, &
-            f_x%x_d, f_y%x_d, f_z%x_d, sens_d, C_NULL_PTR)
+            f_x%x_d, f_y%x_d, f_z%x_d, sens_d, C_NULL_PTR), &
+            'b200_adjrhs_step')
     else
-       ierr = b200_adjrhs_compute(adv%handle, u%x_d, v%x_d, w%x_d, &
+       call b200_check(b200_adjrhs_compute(adv%handle, u%x_d, v%x_d, w%x_d, &
             u_b%x_d, v_b%x_d, w_b%x_d, rho_d, chi_d, fsx_d, fsy_d, fsz_d, &
-            f_x%x_d, f_y%x_d, f_z%x_d, sens_d, C_NULL_PTR)
+            f_x%x_d, f_y%x_d, f_z%x_d, sens_d, C_NULL_PTR), &
+            'b200_adjrhs_compute')
     end if
   end subroutine b200_fused_adjoint_rhs
 

@@ -4,7 +4,9 @@
 !! (sources/neko_ext/math/bcknd/device_math_ext.f90:43-103): device pointers are
 !! `type(c_ptr), value`, scalars are passed by reference.  Every function returns
 !! an integer status (0 = ok); by default the library aborts on error like
-!! `neko_error` / `CUDA_CHECK` do (math_ext.cu:56), so the status can be ignored.
+!! `neko_error` / `CUDA_CHECK` do (math_ext.cu:56).  The shim still passes every
+!! status through `b200_check`, which ends the job with `neko_error` and the
+!! library's message if abort-on-error was switched off.
 !!
 !! NOTE: this file could not be compiled in the build image (no Fortran compiler,
 !! SURVEY.md 0.3); it is checked textually against the C header by
@@ -294,6 +296,22 @@ module neko_top_b200
        integer(c_int64_t) :: classes_in_kernel, classes_total
      end function b200_adjrhs_gs_info
 
+     integer(c_int) function b200_adjrhs_set_xstage(handle, flag) &
+          bind(c, name='b200_adjrhs_set_xstage')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       integer(c_int) :: flag
+     end function b200_adjrhs_set_xstage
+
+     integer(c_int) function b200_adjrhs_xstage_info(handle, active, &
+          linked_elements, classes_left, classes_total) &
+          bind(c, name='b200_adjrhs_xstage_info')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       integer(c_int) :: active
+       integer(c_int64_t) :: linked_elements, classes_left, classes_total
+     end function b200_adjrhs_xstage_info
+
      integer(c_int) function b200_adjrhs_set_dealias(handle, flag) &
           bind(c, name='b200_adjrhs_set_dealias')
        use, intrinsic :: iso_c_binding
@@ -425,6 +443,17 @@ module neko_top_b200
        integer(c_int) :: bnd_elem(*)
      end function b200_adjrhs_set_boundary_elements
 
+     integer(c_int) function b200_gs_init_shared_from_keys(handle, key, &
+          on_device, cand, nshared, nneigh) &
+          bind(c, name='b200_gs_init_shared_from_keys')
+       use, intrinsic :: iso_c_binding
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: key
+       integer(c_int) :: on_device
+       type(c_ptr), value :: cand
+       integer(c_int) :: nshared, nneigh
+     end function b200_gs_init_shared_from_keys
+
      ! ---- diagnostics ------------------------------------------------------
      integer(c_int) function b200_adjrhs_enable_timing(handle, flag) &
           bind(c, name='b200_adjrhs_enable_timing')
@@ -441,5 +470,32 @@ module neko_top_b200
        integer(c_int64_t) :: launches
      end function b200_adjrhs_get_timing
   end interface
+
+contains
+
+  !> Ends the job through `neko_error` when a library call returned non-zero.
+  !! @param ierr   status returned by a `b200_*` function
+  !! @param where  name of the entry point, for the message
+  subroutine b200_check(ierr, where)
+    use utils, only : neko_error
+    integer(c_int), intent(in) :: ierr
+    character(len=*), intent(in) :: where
+    character(kind=c_char), dimension(:), pointer :: cmsg
+    character(len=512) :: msg
+    type(c_ptr) :: p
+    integer :: i
+
+    if (ierr .eq. 0) return
+    msg = ''
+    p = b200_last_error()
+    if (c_associated(p)) then
+       call c_f_pointer(p, cmsg, [512])
+       do i = 1, 512
+          if (cmsg(i) .eq. c_null_char) exit
+          msg(i:i) = cmsg(i)
+       end do
+    end if
+    call neko_error(where // ' failed: ' // trim(msg))
+  end subroutine b200_check
 
 end module neko_top_b200

@@ -22,11 +22,12 @@ contains
   subroutine brinkman_compute_b200(fu, fv, fw, u, v, w, chi)
     type(field_t), intent(inout) :: fu, fv, fw
     type(field_t), intent(in) :: u, v, w, chi
-    integer(c_int) :: ierr, n
+    integer(c_int) :: n
 
     n = fu%dof%size()
-    ierr = b200_brinkman_compute(fu%x_d, fv%x_d, fw%x_d, u%x_d, v%x_d, w%x_d, &
-         chi%x_d, n, glb_cmd_queue)
+    call b200_check(b200_brinkman_compute(fu%x_d, fv%x_d, fw%x_d, u%x_d, v%x_d, w%x_d, &
+         chi%x_d, n, glb_cmd_queue), &
+         'b200_brinkman_compute')
   end subroutine brinkman_compute_b200
 
   !> Body of `adjoint_lube_source_term_compute`
@@ -38,14 +39,15 @@ contains
     real(kind=rp), intent(in) :: K
     type(c_ptr), intent(in) :: mask_d
     integer, intent(in) :: mask_size
-    integer(c_int) :: ierr, n, ms
+    integer(c_int) :: n, ms
     real(c_double) :: Kc
 
     n = fu%dof%size()
     ms = mask_size
     Kc = K
-    ierr = b200_lube_compute(fu%x_d, fv%x_d, fw%x_d, u%x_d, v%x_d, w%x_d, &
-         chi%x_d, Kc, mask_d, ms, n, glb_cmd_queue)
+    call b200_check(b200_lube_compute(fu%x_d, fv%x_d, fw%x_d, u%x_d, v%x_d, w%x_d, &
+         chi%x_d, Kc, mask_d, ms, n, glb_cmd_queue), &
+         'b200_lube_compute')
   end subroutine lube_compute_b200
 
   !> One field of `steady_simcomp_compute` (:158-176): returns the local part of
@@ -56,10 +58,11 @@ contains
     type(field_t), intent(inout) :: x_old
     real(kind=rp) :: res
     real(c_double) :: r
-    integer(c_int) :: ierr, n
+    integer(c_int) :: n
 
     n = x%dof%size()
-    ierr = b200_steady_field_update(r, x%x_d, x_old%x_d, n, glb_cmd_queue)
+    call b200_check(b200_steady_field_update(r, x%x_d, x_old%x_d, n, glb_cmd_queue), &
+         'b200_steady_field_update')
     res = r
   end function steady_update_b200
 

@@ -12,9 +12,9 @@ tests read like tests of the reference (citations relative to /root/reference/so
   steady_simcomp_t                                                    simulation_components/steady_simcomp.f90:49-192
   fused_adjoint_rhs_t  -- the B200 path: adjoint_pnpn.f90:669-682 + :755-757 in one call
 
-The Fortran text a maintainer adds to Neko-TOP is in fortran/ (INTEGRATION.md); the compiled C++
-mirror is csrc/host/neko_top_plugin.hpp.  This Python layer exists because pytest / bench.py drive the
-library; tensors are torch CUDA float64 tensors used purely as device-memory handles.
+The Fortran text a maintainer adds to Neko-TOP is in fortran/ (INTEGRATION.md).  This Python layer exists
+because pytest / bench.py drive the library; tensors are torch CUDA float64 tensors used purely as
+device-memory handles.
 """
 import ctypes as C
 
@@ -430,6 +430,30 @@ class gs_t:
                                              _ci(a[1].size), a[1].ctypes.data_as(ip), a[2].ctypes.data_as(ip),
                                              a[3].ctypes.data_as(ip)))
 
+    def init_shared_from_keys(self, keys, candidates=None):
+        """Shared-node discovery behind the C ABI (b200_gs_init_shared_from_keys; collective over the
+        communicator): keys as in init(), candidates = optional uint8/bool mask of the dofs that can live on
+        another rank (Neko: dm_Xh%shared_dof).  Returns (nshared, nneigh)."""
+        ns, nn = C.c_int(0), C.c_int(0)
+        if isinstance(keys, torch.Tensor) and keys.is_cuda:
+            k = keys.contiguous().view(-1)
+            assert k.dtype == torch.int64 and k.numel() == self._hd.n
+            c = None
+            if candidates is not None:
+                c = candidates.contiguous().view(-1).to(torch.uint8)
+                assert c.is_cuda and c.numel() == self._hd.n
+            check(_lib.lib().b200_gs_init_shared_from_keys(self._hd.h, _ptr(k), _ci(1), _ptr(c), C.byref(ns), C.byref(nn)))
+            torch.cuda.synchronize()
+        else:
+            k = np.ascontiguousarray(np.asarray(keys).reshape(-1), dtype=np.int64)
+            cp = None
+            if candidates is not None:
+                c = np.ascontiguousarray(np.asarray(candidates).reshape(-1), dtype=np.uint8)
+                cp = c.ctypes.data_as(C.c_void_p)
+            check(_lib.lib().b200_gs_init_shared_from_keys(self._hd.h, k.ctypes.data_as(C.POINTER(C.c_int64)), _ci(0),
+                                                           cp, C.byref(ns), C.byref(nn)))
+        return ns.value, nn.value
+
 
 # ---- the fused B200 path -----------------------------------------------------------------------------------
 class fused_adjoint_rhs_t:
@@ -511,6 +535,16 @@ class fused_adjoint_rhs_t:
         a, b, c = C.c_int(0), C.c_int64(0), C.c_int64(0)
         check(_lib.lib().b200_adjrhs_gs_info(self._hd.h, C.byref(a), C.byref(b), C.byref(c)))
         return bool(a.value), b.value, c.value
+
+    def set_xstage(self, flag=True):
+        """i-face pair classes of consecutive elements summed inside the lx = 8 element kernel (default on)."""
+        check(_lib.lib().b200_adjrhs_set_xstage(self._hd.h, _ci(flag)))
+
+    def xstage_info(self):
+        """(active, elements linked to their predecessor, classes left to the gs pass, classes in total)."""
+        a, b, c, d = C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().b200_adjrhs_xstage_info(self._hd.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return bool(a.value), b.value, c.value, d.value
 
     def enable_timing(self, flag=True):
         check(_lib.lib().b200_adjrhs_enable_timing(self._hd.h, _ci(flag)))

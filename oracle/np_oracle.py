@@ -210,3 +210,21 @@ def gs_add(f, key):
     acc = np.zeros(inv.max() + 1)
     np.add.at(acc, inv, f)
     return acc[inv]
+
+
+def steady_simcomp_compute(fields, olds, tol):
+    """simulation_components/steady_simcomp.f90:154-188 restated: old -= new (field_sub2, :155-161),
+    normed_diff = glsc2(old, old) per field (:165-173), then EITHER old = new (field_copy, :178-186) when
+    max(normed_diff) > tol OR freeze (:188).  `olds` is updated in place like the reference's this%u_old ...;
+    returns (normed_diff list, freeze).  Sums are left-to-right in float64 extended by math.fsum (exact), the
+    CUDA path's deterministic tree differs from it only by rounding."""
+    import math
+    normed = []
+    for f, o in zip(fields, olds):
+        o -= f
+        normed.append(math.fsum((o * o).tolist()))
+    freeze = not (max(normed) > tol)
+    if not freeze:
+        for f, o in zip(fields, olds):
+            o[:] = f
+    return normed, freeze

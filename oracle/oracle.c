@@ -29,6 +29,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py sets the thread count explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ============================ speclib ======================================================= */
 
 /* Legendre polynomial P_n(x) and derivative by the three-term recurrence. */

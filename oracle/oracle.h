@@ -184,6 +184,7 @@ int64_t orc_gs_classes(int64_t *class_id, const int64_t *key, int64_t n);
 void orc_gs_add(double *f, const int64_t *class_id, int64_t nclass, int64_t n);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

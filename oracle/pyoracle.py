@@ -66,6 +66,12 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP threads of the element loops (bench.py: all host cores, whatever OMP_NUM_THREADS says)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 # ---- speclib ----
 def zwgll(n):
     z, w = np.zeros(n), np.zeros(n)

@@ -80,8 +80,7 @@ def test_fortran_shim_binds_every_symbol():
 
 def test_c99_consumer_links_and_runs(L):
     """csrc/host/abi_check.c (C99, -pedantic -Werror) includes the header, takes the address of every declared
-    entry point, links against the shared library and exercises the no-abort error path; the C++17 mirror
-    header csrc/host/neko_top_plugin.hpp must compile against the same header.  No GPU needed."""
+    entry point, links against the shared library and exercises the no-abort error path.  No GPU needed."""
     import subprocess
     host = os.path.join(ROOT, "neko-top_b200", "csrc", "host")
     subprocess.check_call(["make", "-B", "-C", host], stdout=subprocess.DEVNULL)

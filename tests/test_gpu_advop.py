@@ -289,3 +289,76 @@ def test_pde_filter(oracle, lx, precond):
     flt.apply_backward(g, x_in)
     assert rel_l2(g.cpu().numpy(), ref) <= 1e-9
     op.free()
+
+
+def test_steady_simcomp(oracle):
+    """steady_simcomp_t%compute_ (simulation_components/steady_simcomp.f90:154-188) through
+    b200_steady_field_update: squared norm of the change per field against the oracle restatement, old <- new,
+    freeze once below the tolerance, and a run-to-run deterministic reduction (same bits)."""
+    from oracle import np_oracle as npo
+    ops = _ops()
+    rng = np.random.default_rng(21)
+    n = 3 * 8 ** 3 * 37 + 5                      # not a multiple of anything in the kernel
+    new = [rng.standard_normal(n) for _ in range(4)]          # u, v, w, p
+    old0 = [a + 1e-4 * rng.standard_normal(n) for a in new]
+    d_new = [torch.as_tensor(a).cuda() for a in new]
+    sc = ops.steady_simcomp_t()
+    sc.init_from_attributes(1e-12, d_new)
+    for o, src in zip(sc.old, old0):
+        o.copy_(torch.as_tensor(src))
+    old_np = [a.copy() for a in old0]
+    nd_ref, fr_ref = npo.steady_simcomp_compute(new, old_np, 1e-12)
+    sc.compute_()
+    assert sc.freeze == fr_ref == False
+    for a, b in zip(sc.normed_diff, nd_ref):
+        assert abs(a - b) <= 1e-13 * abs(b)
+    for o, a in zip(sc.old, d_new):
+        assert torch.equal(o, a)
+    # determinism: the same update from the same state gives the same bits
+    vals = []
+    for _ in range(3):
+        for o, src in zip(sc.old, old0):
+            o.copy_(torch.as_tensor(src))
+        sc.compute_()
+        vals.append(tuple(sc.normed_diff))
+    assert vals[0] == vals[1] == vals[2]
+    # unchanged fields -> zero change -> freeze, and a frozen component does nothing
+    sc.compute_()
+    assert sc.freeze and max(sc.normed_diff) == 0.0
+    # empty field
+    e = torch.empty(0, device="cuda", dtype=torch.float64)
+    sc2 = ops.steady_simcomp_t()
+    sc2.init_from_attributes(1.0, [e])
+    sc2.compute_()
+    assert sc2.normed_diff == [0.0] and sc2.freeze
+
+
+def test_step_host_dealias_chunks(oracle):
+    """b200_adjrhs_step_host with the dealiased operator and several element chunks (nelv >= 512): every chunk
+    must compute ITS elements (the fine-grid operator honours the chunk's first element), result identical to
+    the device-resident step and within 1e-12 of the oracle."""
+    lx = 6
+    P = Problem(lx, ne=(8, 8, 9), deform=0.02)            # 576 elements -> 2 chunks
+    ops = _ops()
+    coef = ops.coef_t(ops.space_t(P.lx, P.D, P.w), P.nelv, P.cuda("G"), P.cuda("B"))
+    op = ops.fused_adjoint_rhs_t(coef)
+    op.gs.init(P.keys.reshape(-1).cuda())
+    op.set_dealias(True)
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    nan = lambda: torch.full((P.n,), float("nan"), device="cuda", dtype=torch.float64)
+    f, sens = [nan() for _ in range(3)], nan()
+    op.step(v, ub, f, rho=rho, sens=sens)
+    hv = [a.cpu().pin_memory() for a in v]
+    hub = [a.cpu().pin_memory() for a in ub]
+    hf = [torch.full((P.n,), float("nan"), dtype=torch.float64).pin_memory() for _ in range(3)]
+    hs = torch.full((P.n,), float("nan"), dtype=torch.float64).pin_memory()
+    op.step_host(hv, hub, rho.cpu().pin_memory(), hf, hs)
+    for c in range(3):
+        assert torch.equal(hf[c], f[c].cpu()), "host-buffer step (chunked, dealiased) differs from the device step"
+    assert torch.equal(hs, sens.cpu())
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho, lxd=3 * lx // 2)
+    cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
+    for c in range(3):
+        assert rel_l2(hf[c].numpy(), oracle.gs_add(fo[c], cid, nc)) <= 1e-12
+    assert rel_l2(hs.numpy(), so) <= 1e-12
+    op.free()

@@ -306,6 +306,43 @@ def test_full_size_properties():
     op.free()
 
 
+def test_config1_full_size_vs_oracle(oracle):
+    """BASELINE configs[1] at FULL size (32^3 elements, lx = 8, 16.8 MDOF; random design field, RAMP 0/1000/1
+    convex-up, K = 1) compared directly with the oracle: f after gs_op and the sensitivity <= 1e-12, and the
+    gather-scatter class map integer-identical on the whole mesh."""
+    from neko_top_b200 import sem, workloads
+    ops = _ops()
+    lx, ne = 8, 32
+    brick = workloads.config_box(ne, lx)
+    sp = sem.Space(lx)
+    x, y, z = workloads.coords(brick, "cuda")
+    keys = workloads.node_keys(brick, "cuda")
+    G, _, B = sem.geometric_factors(x, y, z, sp)
+    fl = workloads.make_fields(brick, x, y, z, keys)
+    del x, y, z
+    flat = lambda a: a.reshape(-1).contiguous()
+    Gf, Bf = [flat(g) for g in G], flat(B)
+    v, ub, rho, kf = [flat(a) for a in fl.v], [flat(a) for a in fl.ub], flat(fl.rho), flat(keys)
+    op = ops.fused_adjoint_rhs_t(ops.coef_t(ops.space_t(lx, sp.dx, sp.wx), brick.nelv, Gf, Bf))
+    op.set_params()
+    op.gs.init(kf)
+    n = brick.n
+    f, sens = [_nan(n) for _ in range(3)], _nan(n)
+    op.step(v, ub, f, rho=rho, sens=sens)
+    active, nlinked, _, _ = op.xstage_info()
+    assert active and nlinked > 0.9 * brick.nelv * (ne - 1) / ne
+    c = lambda t: t.cpu().numpy()
+    fo, so, _ = oracle.adjoint_rhs([c(a) for a in v], [c(a) for a in ub], lx, brick.nelv, sp.dx, sp.wx,
+                                   [c(g) for g in Gf], c(Bf), rho=c(rho))
+    cid, nc = oracle.gs_classes(c(kf))
+    gcid, gnc = op.gs.classes()
+    assert gnc == nc and np.array_equal(gcid, cid), "gather-scatter index map differs from the oracle's at 32^3"
+    for k in range(3):
+        assert rel_l2(c(f[k]), oracle.gs_add(fo[k], cid, nc)) <= TOL
+    assert rel_l2(c(sens), so) <= TOL
+    op.free()
+
+
 def _check_step_host(op, v, ub, rho, f, sens):
     """b200_adjrhs_step_host (host buffers; several element chunks, summation and copies pipelined when the
     elements are in mesh order) must reproduce the device-resident step bit for bit."""
@@ -356,6 +393,60 @@ def test_step_gs_in_kernel(oracle, order_kind):
         for c in range(3):
             assert torch.equal(f[c], g[c]), f"gs mode 2 and mode {mode} must be bit-identical"
     _check_step_host(op, v, ub, rho, f, sens)
+    op.free()
+
+
+@pytest.mark.parametrize("kind", ["box", "ragged", "folded_keys", "x_periodic"])
+def test_step_xstage(oracle, kind):
+    """lx = 8 default step: every slot walks a contiguous run of elements and sums the i-face pair classes of
+    consecutive elements in the kernel; the pass runs over the classes that are left.  Must be BIT-identical to
+    the plain kernel + full pass, and within 1e-12 of the oracle; links are only taken where the classes
+    really are aligned pairs."""
+    lx = 8
+    ne = {"box": (12, 10, 9), "ragged": (7, 67, 1), "folded_keys": (9, 8, 7), "x_periodic": (16, 8, 5)}[kind]
+    P = Problem(lx, ne=ne, deform=0.02)
+    keys = P.keys.reshape(-1).numpy().copy()
+    if kind == "folded_keys":          # unrelated nodes identified: some face pairs become 3+ member classes
+        rng = np.random.default_rng(23)
+        sel = rng.random(keys.size) < 0.01
+        keys[sel] = keys.max() + 1 + rng.integers(0, sel.sum() // 3 + 1, sel.sum())
+    if kind == "x_periodic":           # i = 7 face of the last element of a row glued to i = 0 of the first
+        k4 = keys.reshape(ne[2], ne[1], ne[0], lx, lx, lx)       # [ez, ey, ex, k, j, i]
+        k4[:, :, -1, :, :, -1] = k4[:, :, 0, :, :, 0]
+        keys = k4.reshape(-1)
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    cid, nc = oracle.gs_classes(keys)
+    op, _ = _fused(P)
+    op.gs.init(keys)
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+    for _ in range(2):
+        op.step(v, ub, f, rho=rho, sens=sens)
+    active, nlinked, nleft, ntot = op.xstage_info()
+    assert active and 0 < nlinked < P.nelv and nleft == ntot - 36 * nlinked
+    if kind == "box":
+        nslots = 444 if P.nelv >= 444 else P.nelv
+        # every element but the first of an x-row, minus the run starts of the element slots
+        assert (ne[0] - 1) * ne[1] * ne[2] - nslots <= nlinked <= (ne[0] - 1) * ne[1] * ne[2]
+    for c in range(3):
+        assert rel_l2(f[c].cpu().numpy(), oracle.gs_add(fo[c], cid, nc)) <= TOL
+    assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    op.set_xstage(False)
+    g, sens2 = [_nan(P.n) for _ in range(3)], _nan(P.n)
+    op.step(v, ub, g, rho=rho, sens=sens2)
+    assert not op.xstage_info()[0]
+    for c in range(3):
+        assert torch.equal(f[c], g[c]), "x stage must be bit-identical to the plain kernel + full pass"
+    assert torch.equal(sens, sens2)
+    # static forcing (the NF_FULL kernel variant) through the x stage too
+    op.set_xstage(True)
+    fs = [torch.as_tensor(np.random.default_rng(4).standard_normal(P.n)).cuda() for _ in range(3)]
+    f3, g3 = [_nan(P.n) for _ in range(3)], [_nan(P.n) for _ in range(3)]
+    op.step(v, ub, f3, rho=rho, fstatic=fs)
+    op.set_xstage(False)
+    op.step(v, ub, g3, rho=rho, fstatic=fs)
+    for c in range(3):
+        assert torch.equal(f3[c], g3[c])
     op.free()
 
 

@@ -353,3 +353,17 @@ def test_helmholtz_operator_restatement(oracle):
     xf = oracle.pde_filter_dense(P.rho, lx, P.nelv, P.D, P.w, P.G, jacinv, P.B, cid, nc, 0.1)
     assert P.rho.min() < xf.min() and xf.max() < P.rho.max()
     assert np.abs(oracle.pde_filter_dense(one, lx, P.nelv, P.D, P.w, P.G, jacinv, P.B, cid, nc, 0.1) - 1.0).max() <= 1e-12
+
+
+def test_steady_simcomp_restatement():
+    """steady_simcomp.f90:154-188: squared norm of the change per field, copy-or-freeze."""
+    from oracle import np_oracle as npo
+    rng = np.random.default_rng(11)
+    new = [rng.standard_normal(1000) for _ in range(4)]
+    old = [a + 1e-3 * rng.standard_normal(1000) for a in new]
+    expect = [float(np.sum((o - a) ** 2)) for a, o in zip(new, old)]
+    nd, freeze = npo.steady_simcomp_compute(new, old, tol=1e-9)
+    assert not freeze and np.allclose(nd, expect, rtol=1e-13)
+    assert all(np.array_equal(o, a) for a, o in zip(new, old)), "old fields must be overwritten by the new ones"
+    nd, freeze = npo.steady_simcomp_compute(new, old, tol=1e-9)
+    assert freeze and max(nd) == 0.0

@@ -45,15 +45,27 @@ def main():
     idb = [ops.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(idb, src=0)
     op.comm_init(idb[0], rank, world)
-    sh = partition.find_shared_nodes(d["keys"], workloads.interface_candidates(brick, dev), lx ** 3, rank, world)
-    op.gs.init_shared(sh.shared_dof, sh.neigh_rank, sh.neigh_off, sh.neigh_idx)
+    # discovery behind the C ABI (device + ncclAllGather), cross-checked against the torch.distributed host
+    # implementation the CPU (gloo) tests cover
+    cand = workloads.interface_candidates(brick, dev)
+    sh = partition.find_shared_nodes(d["keys"], cand, lx ** 3, rank, world)
+    ns_abi, nn_abi = op.gs.init_shared_from_keys(d["keys"], cand)
+    assert ns_abi == sh.nshared and nn_abi == sh.neigh_rank.size, (ns_abi, sh.nshared, nn_abi, sh.neigh_rank.size)
+    if world == 2:        # no candidate mask: every element-surface dof is a candidate
+        ns2, nn2 = op.gs.init_shared_from_keys(d["keys"].cpu().numpy(), None)
+        assert (ns2, nn2) == (ns_abi, nn_abi)
     n = brick.n
     mk = lambda: [torch.full((n,), float("nan"), device=dev, dtype=torch.float64) for _ in range(3)]
     results = {}
-    for mode in ("sequential", "overlap", "overlap_gs1", "overlap_gs2"):
+    for mode in ("sequential", "no_xstage", "overlap", "overlap_gs1", "overlap_gs2"):
         # sequential = the default path (exchange overlapped with the local gs); with
         # B200_EXCHANGE_OVERLAP=elem the "overlap*" modes run the boundary/interior split
+        if mode == "sequential":
+            op.set_xstage(True)
+        if mode == "no_xstage":                # plain element kernel + full local pass
+            op.set_xstage(False)
         if mode == "overlap":
+            op.set_xstage(True)
             op.set_boundary_elements(sh.bnd_elem)
         if mode.startswith("overlap_gs"):      # packed class lists / summation inside the interior kernel
             op.set_gs_mode(int(mode[-1]))
@@ -61,6 +73,8 @@ def main():
         for _ in range(2):
             op.step(d["v"], d["ub"], f, rho=d["rho"], sens=sens)
         torch.cuda.synchronize()
+        if mode == "sequential":
+            xs_info = op.xstage_info()
         results[mode] = [a.cpu().numpy() for a in f] + [sens.cpu().numpy()]
     # host-buffer path
     hv = [a.cpu().pin_memory() for a in d["v"]]
@@ -94,19 +108,23 @@ def main():
             worst = max(worst, err)
         print(f"rank {rank} {mode}: max rel-L2 vs global oracle = {worst:.3e}", flush=True)
     op.set_gs_mode(0)
-    same = all(np.array_equal(a, b) for m in ("overlap", "overlap_gs1", "overlap_gs2")
+    same = all(np.array_equal(a, b) for m in ("no_xstage", "overlap", "overlap_gs1", "overlap_gs2")
                for a, b in zip(results["sequential"], results[m]))
     same_h = all(np.array_equal(a, b) for a, b in zip(results["sequential"], results["host"]))
     t = torch.tensor([worst, 0.0 if (same and same_h) else 1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = True
     if rank == 0:
         ok = t[0].item() <= 1e-12 and t[1].item() == 0.0
         print(f"MGPU_CHECK world={world} ne={ne} lx={lx} nshared(rank0)={sh.nshared} nbnd(rank0)={sh.bnd_elem.size} "
+              f"xstage(rank0: active, linked elements, classes left, total)={xs_info} "
               f"max_err={t[0].item():.3e} modes_bit_identical={t[1].item() == 0.0} -> {'PASS' if ok else 'FAIL'}",
               flush=True)
     op.free()
     dist.barrier()
     dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -193,13 +193,19 @@ def parity_vs_oracle(prob, f_dev, sens_dev, ne_gpu, oracle_out=None, tol=1e-12):
         cut.append(on_cut.expand(b.nelv, lx, lx, lx))
     inside = ~(cut[0] | cut[1] | cut[2]).reshape(-1).numpy()
     rel = lambda a, r: float(np.linalg.norm(a - r) / max(np.linalg.norm(r), 1e-300))
-    errs = []
+    errs, worst_pt = [], (0.0, -1, -1)
     for c in range(3):
         got = f_dev[c].view(-1, N)[idx].reshape(-1).cpu().numpy()
         errs.append(rel(got[inside], oracle_out["f"][c][inside]))
+        d = np.abs(got - oracle_out["f"][c]) * inside
+        j = int(np.argmax(d))
+        if d[j] > worst_pt[0]:
+            worst_pt = (float(d[j]), c, j)
     es = rel(sens_dev.view(-1, N)[idx].reshape(-1).cpu().numpy(), oracle_out["sens"])
     worst = max(max(errs), es)
     return {"rel_l2_f": max(errs), "rel_l2_sens": es, "n_dof_checked": int(inside.sum()), "tol": tol,
+            "max_abs_err_f": {"value": worst_pt[0], "component": worst_pt[1], "sample_element": worst_pt[2] // N,
+                              "node": worst_pt[2] % N},
             "ok": bool(np.isfinite(worst) and worst <= tol),
             "against": "oracle/oracle.c on the " + prob["desc"] + "; f after gs on the nodes whose class lies inside "
                        "the sample, sens on all of it"}

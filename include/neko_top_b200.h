@@ -197,15 +197,21 @@ int b200_mask_exterior_const(void* fld, void* work, const void* mask_d, const in
  * PDE_filter_t%apply / %apply_backward (mapping_functions/PDE_filter_mapping.f90:212-363): solve
  *   (r^2 K + M) x = gs(B * x_in)        (coef%h1 = r^2, coef%h2 = 1, ifh2; no Dirichlet conditions)
  * with Neko's preconditioned conjugate gradients (ax_helm, gs_op on every operator application, inner products
- * weighted with coef%mult, zero initial guess, stop when sqrt(r.mult.r)*norm_fac < abs_tol).  Both directions of
- * the filter are this call (the backward pass filters the sensitivity with the same operator).
- * jacinv = coef%jacinv_d, mult = coef%mult_d; *precond: 0 = ident, otherwise jacobi (diagonal without the
- * cross terms of deformed elements); norm_fac = 1/sqrt(volume) as in Neko, NULL = 1.  In a multi-GPU run the
- * inner products are summed over the ranks with ncclAllReduce.  Needs b200_gs_init. */
+ * weighted with coef%mult, stop when sqrt(r.mult.r)*norm_fac < abs_tol).  The reference selects "gmres" + "ident"
+ * (:133-137); the operator is symmetric positive definite, so CG converges to the same solution within the same
+ * tolerance -- only ksp_results%iter differs (documented deviation).  Both directions of the filter are
+ * this call (the backward pass filters the sensitivity with the same operator).
+ * jacinv = coef%jacinv_d, mult = coef%mult_d; *precond: 0 = ident (the reference's choice), otherwise jacobi
+ * (diagonal without the cross terms of deformed elements); norm_fac = 1/sqrt(volume) as in Neko, NULL = 1;
+ * *x0_is_input != 0: start from x = x_in ("copy the unfiltered design as an initial guess", :246-248), 0 or NULL:
+ * from x = 0 (what Neko's Krylov solvers do on entry).  The whole iteration runs on the device: inner products
+ * are deterministic two-stage reductions into a device scalar (ncclAllReduce over the ranks in a multi-GPU run),
+ * alpha / beta never visit the host, and the host looks at the residual once every 8 iterations (kernels past
+ * convergence are no-ops, so the result is that of stopping at the exact iteration).  Needs b200_gs_init. */
 int b200_pde_filter_apply(void* handle, void* x_out, const void* x_in, const void* jacinv, const void* mult,
                           const double* radius, const double* abs_tol, const int* max_iter,
-                          const int* precond, const double* norm_fac, int* iters, double* res_start,
-                          double* res_final);
+                          const int* precond, const double* norm_fac, const int* x0_is_input, int* iters,
+                          double* res_start, double* res_final);
 
 /* ---- explicit time scheme around the RHS (adjoint/adjoint_pnpn.f90:665-666,688-696) --
  * Neko's rhs_maker types, argument order of the reference's call sites; all fields are device pointers of

@@ -64,7 +64,6 @@ struct KParams2 {
   int gs_lag;                 // windows between storing an element and summing its classes (>= 1)
   int elem_base;              // v2: added to every element index (field pointers stay 16-byte aligned for odd LX)
   const unsigned char* xlink; // v3 XS: xlink[e] != 0: faces (e-1: i=7) and (e: i=0) are glued node by node
-  int xs_shift;               // v3 XS: log2 of the run length inside a window (>= 30: one contiguous run per slot)
 };
 
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {

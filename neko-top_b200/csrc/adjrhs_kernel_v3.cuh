@@ -30,14 +30,14 @@
 // Arithmetic = adjrhs_common.cuh header.
 //
 // XS ("x stage", profiles/README.md r02): the separate gather-scatter pass re-reads and re-writes ALL of f because
-// every 32-byte sector of an element holds a node of an i-face (i = 0 or 7).  With XS each slot processes a
-// CONTIGUOUS run of elements, and where element e-1 and e are glued i=7 -> i=0 with identical (j,k) orientation
+// every 32-byte sector of an element holds a node of an i-face (i = 0 or 7).  With XS each slot processes runs of
+// consecutive elements, and where element e-1 and e are glued i=7 -> i=0 with identical (j,k) orientation
 // (p.xlink[e], verified against the gather-scatter classes at set-up) the 36 face-interior pair classes are
-// summed here: lane (g,3) keeps the previous element's i = 7 values of its planes in shared memory, one
-// shfl.xor(3) pairs it with lane (g,0), which adds the partner to its i = 0 value before the regular store,
-// while lane (g,3) rewrites the previous element's i = 7 value (an 8-byte store into a line that is still in
-// L2).  a + b is commutative, so both copies are bit-identical to the oracle's (0 + a) + b.  The pass that
-// follows skips these classes and then touches only the rows j = 0,7 / planes k = 0,7: 44 % of the sectors.
+// summed here: before its regular 128-bit store, lane (g,0) re-loads the previous element's i = 7 value of its
+// row (stored one iteration earlier by lane (g,3): an L2 hit, __ldcg), adds it to its own i = 0 value and
+// rewrites the partner with the same sum (8-byte store into a line that is still in L2).  a + b is
+// commutative, so both copies are bit-identical to the oracle's (0 + a) + b.  The pass that follows skips
+// these classes and then touches only the rows j = 0,7 / planes k = 0,7: 44 % of the sectors.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -58,10 +58,14 @@ struct V3Cfg {
   static constexpr int STAGE_BYTES = NF * PLANE_BYTES;
   static constexpr int SLOT_BYTES = WT_BYTES + SCR_BYTES + NW * DS * STAGE_BYTES;
   static constexpr int BAR_OFF = NE * SLOT_BYTES;
-  static constexpr int SMEM = BAR_OFF + 8 * NE * NW * DS + 16;
-  static constexpr int X7_BYTES = 3 * 64 * 8;                // XS: previous element's i = 7 values [c][k][j]
-  static constexpr int SMEM_XS = SMEM + NE * X7_BYTES;
-  static_assert(SMEM % 16 == 0, "X7 area must stay 8-byte aligned");
+  // per-lane constants (fragments of D, quadrature weights) live in shared memory, [value][lane]: read from the
+  // constant bank with a lane-dependent index they cost one ADU pass per distinct address (32 per warp), and the
+  // compiler re-loads them every iteration instead of keeping 20 registers -- ncu r02e: the ADU pipe was the
+  // busiest unit of the kernel (54 %) before this table
+  static constexpr int CT_OFF = BAR_OFF + 8 * NE * NW * DS + 16;
+  static constexpr int CT_VALS = 10;
+  static constexpr int SMEM = CT_OFF + CT_VALS * 32 * 8;
+  static_assert(CT_OFF % 16 == 0, "constant table must be 16-byte aligned");
   static_assert(8 % NW == 0, "NW must divide 8");
 };
 
@@ -207,23 +211,16 @@ __device__ __forceinline__ void gs_batch(const KParams2<8>& p, int pos0, int nsl
   }
 }
 
-// element -> (slot, iteration) map of the XS kernels; shared with the set-up (capi.cu build_xstage)
-struct XsMap { int nfull, tail0, rem; };
-__host__ __device__ __forceinline__ XsMap xs_map(int nelem, int nslots, int shift) {
-  XsMap m;
-  const long long W = (long long)nslots << shift;           // elements per full window
-  m.nfull = (int)(nelem / W);
-  m.tail0 = (int)(m.nfull * W);
-  m.rem = nelem - m.tail0;
-  return m;
+// element -> slot map of the XS kernels, shared with the set-up (capi.cu build_xstage): slot s of nslots owns
+// the contiguous run [xs_run_begin(s), xs_run_begin(s + 1)) -- balanced to +-1 element.  (Windows of shorter
+// runs per slot were measured too, r02c/r02f: no faster, and they link fewer faces.)
+__host__ __device__ __forceinline__ int xs_run_begin(int s, int nelem, int nslots) {
+  return (int)(((long long)s * nelem) / nslots);
 }
-// true if element e is the first of a run (its predecessor e-1 is processed by another slot, or much earlier)
-__host__ __device__ __forceinline__ bool xs_is_run_start(int e, int nelem, int nslots, int shift) {
-  const XsMap m = xs_map(nelem, nslots, shift);
-  if (e < m.tail0) return (e & ((1 << shift) - 1)) == 0;
-  const int t = e - m.tail0;                                 // balanced runs of the tail: starts floor(s*rem/nslots)
-  const long long sidx = ((long long)t * nslots + m.rem - 1) / m.rem;
-  return (sidx * m.rem) / nslots == t;
+// true if element e is the first of a run (its predecessor e-1 belongs to another slot)
+__host__ __device__ __forceinline__ bool xs_is_run_start(int e, int nelem, int nslots) {
+  const long long sidx = ((long long)e * nslots + nelem - 1) / nelem;      // smallest s with run_begin(s) >= e
+  return (sidx * nelem) / nslots == e;
 }
 
 // GS: compile the in-kernel summation in (FLAG_GS is then honoured); HINT: evict_first policy on the inputs
@@ -232,8 +229,8 @@ template <int NE, int NW, int DS, int NF, int MAXREG, bool GS = false, bool HINT
 __global__ void __launch_bounds__(V3Cfg<NE, NW, DS, NF>::NTHREADS, 1) __maxnreg__(MAXREG)
 adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   using C = V3Cfg<NE, NW, DS, NF>;
-  // XS = 1: exchange through shfl + shared memory; XS = 2: lane (g,0) re-loads the previous element's i = 7 value
-  // from L2 (__ldcg) and rewrites it -- no cross-lane traffic
+  // XS = 2: lane (g,0) re-loads the previous element's i = 7 value from L2 (__ldcg) and rewrites it -- no cross-lane
+  // traffic (XS = 1, an exchange through shfl + shared memory, measured 5 % slower, is gone)
   static_assert(!XS || (!GS && !LIST), "the x stage runs on contiguous element runs without the in-kernel gs");
   constexpr int LX = 8, N = 512, PLANE = 64;
   constexpr int NPL = LX / NW;        // planes per warp
@@ -246,6 +243,18 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   if (tid == 0) {
     for (int i = 0; i < NE * NW * DS; i++) mbar_init(&bars[i], 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    double* ct = reinterpret_cast<double*>(smem + C::CT_OFF) + tid;
+    const int tg = tid >> 2, tq = tid & 3;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      ct[(0 + s) * 32] = p.D[tg + 8 * (2 * tq + s)];       // B frag, forward r:   D(i=g, m=2q+s)
+      ct[(2 + s) * 32] = p.D[tg + 8 * (tq + 4 * s)];       // A frag, forward s/t: D(row=g, m=q+4s)
+      ct[(4 + s) * 32] = p.D[(2 * tq + s) + 8 * tg];       // B frag, transposed r:   D(m=2q+s, i=g)
+      ct[(6 + s) * 32] = p.D[(tq + 4 * s) + 8 * tg];       // A frag, transposed s/t: D(m=q+4s, row=g)
+      ct[(8 + s) * 32] = p.w[2 * tq + s] * p.w[tg];        // w_i w_j of the lane's points
+    }
   }
   __syncthreads();
 
@@ -268,17 +277,11 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   const int bar_id = 1 + slot;
   const unsigned flags = p.flags;
 
-  // constant fragments of the derivative matrix D(i,m) = p.D[i + 8m]
-  double DrF[2], DsF[2], DrB[2], DsB[2];
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    DrF[s] = p.D[g + 8 * (2 * q + s)];       // B frag, forward r:   D(i=g, m=2q+s)
-    DsF[s] = p.D[g + 8 * (q + 4 * s)];       // A frag, forward s/t: D(row=g, m=q+4s)
-    DrB[s] = p.D[(2 * q + s) + 8 * g];       // B frag, transposed r:   D(m=2q+s, i=g)
-    DsB[s] = p.D[(q + 4 * s) + 8 * g];       // A frag, transposed s/t: D(m=q+4s, row=g)
-  }
-  const double wj = p.w[g];
-  const double wij0 = p.w[2 * q] * wj, wij1 = p.w[2 * q + 1] * wj;
+  // constant fragments of the derivative matrix D(i,m) = p.D[i + 8m] and the (i,j) quadrature weights of the
+  // lane's two points: table in shared memory, filled once by the first warp
+  enum : int { CT_DRF = 0, CT_DSF = 2, CT_DRB = 4, CT_DSB = 6, CT_WIJ = 8 };
+  const double* ctab = reinterpret_cast<const double*>(smem + C::CT_OFF) + lane;
+#define CT(v) ctab[(v) * 32]
 
   // per-lane static offsets
   const int pl2 = 2 * q + 8 * g;                 // own point pair inside a plane (doubles)
@@ -287,23 +290,17 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   const int scr_r0 = scr_off(g, q), scr_r1 = scr_off(g, q + 4);
 
   const int g0 = (int)blockIdx.x * NE + slot;
-  // XS: slot g0 owns the contiguous run [e_first, e_first + n_my) (balanced to +-1 element); otherwise the
-  // elements g0, g0 + nslots, ... (the grid works on a window of nslots consecutive elements)
-  [[maybe_unused]] int e_first = 0, xs_full = 0;
+  // XS: slot g0 owns the contiguous run [e_first, e_first + n_my); otherwise the elements g0, g0 + nslots, ...
+  // (the grid works on a window of nslots consecutive elements)
+  [[maybe_unused]] int e_first = 0;
   int n_my_;
   if constexpr (XS) {
-    // windows of nslots runs of R = 2^xs_shift consecutive elements (neighbouring slots stay close in memory);
-    // the elements after the last full window are shared out as one balanced contiguous run per slot
-    const XsMap m = xs_map(p.nelem, nslots, p.xs_shift);
-    xs_full = m.nfull << p.xs_shift;                                      // iterations inside full windows
-    e_first = m.tail0 + (int)(((long long)g0 * m.rem) / nslots);          // first element of the tail run
-    n_my_ = xs_full + (int)(((long long)(g0 + 1) * m.rem) / nslots) - (e_first - m.tail0);
+    e_first = xs_run_begin(g0, p.nelem, nslots);
+    n_my_ = xs_run_begin(g0 + 1, p.nelem, nslots) - e_first;
   } else {
     n_my_ = (p.nelem > g0) ? (p.nelem - 1 - g0) / nslots + 1 : 0;
   }
   const int n_my = n_my_;
-  [[maybe_unused]] double* x7 = nullptr;
-  if constexpr (XS == 1) x7 = reinterpret_cast<double*>(smem + C::SMEM + slot * C::X7_BYTES);
   const int n_planes = n_my * NPL;               // planes this warp will consume
   const uint32_t stage_tx = (uint32_t)p.n_active * C::PLANE_BYTES;
 
@@ -316,10 +313,6 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     if constexpr (LIST) { if (itx < n_my) en = __ldg(p.elem_list + en); }
     return en;
   };
-  auto xs_elem = [&](int itx) {
-    if (itx >= xs_full) return e_first + (itx - xs_full);
-    return (((itx >> p.xs_shift) * nslots + g0) << p.xs_shift) + (itx & ((1 << p.xs_shift) - 1));
-  };
   [[maybe_unused]] int it_now = 0;
   [[maybe_unused]] int e_cur = 0, e_nxt = 0;
   if constexpr (LIST) { e_cur = elem_at(0); e_nxt = elem_at(1); }
@@ -328,7 +321,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     const int itn = n / NPL, pin = n - itn * NPL;      // itn is it_now or it_now + 1 (DS <= NPL)
     int en;
     if constexpr (LIST) en = (itn == it_now) ? e_cur : e_nxt;
-    else if constexpr (XS) en = xs_elem(itn);
+    else if constexpr (XS) en = e_first + itn;
     else en = g0 + itn * nslots;
     const size_t goff = (size_t)en * N + (size_t)(wid + pin * NW) * PLANE;
     unsigned char* dst = ring + (n % DS) * C::STAGE_BYTES;
@@ -384,7 +377,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   for (int it = 0; it < n_my; it++) {
     int e;
     if constexpr (LIST) { it_now = it; e = e_cur; }
-    else if constexpr (XS) e = xs_elem(it);
+    else if constexpr (XS) e = e_first + it;
     else e = g0 + it * nslots;
     const size_t ebase = (size_t)e * N;
     // xlink[e] != 0: e's i = 0 face is glued to the i = 7 face of element e-1, and e-1 is the element this slot
@@ -400,8 +393,8 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       const double* __restrict__ Uc = p.ub[c] + ebase + 8 * j + g;
       const double b0 = __ldg(Uc + 64 * q), b1 = __ldg(Uc + 64 * (q + 4));
       double2 acc = make_double2(0.0, 0.0);
-      dmma(acc, DsF[0], b0);
-      dmma(acc, DsF[1], b1);
+      dmma(acc, CT(CT_DSF), b0);
+      dmma(acc, CT(CT_DSF + 1), b1);
       *reinterpret_cast<double2*>(Wt + c * N + wt_off(2 * q, j, g)) = acc;
     }
     named_bar_sync(bar_id, C::NSLOT_THR);
@@ -413,17 +406,18 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       const int k = wid + pi * NW;
       const int qoff = 64 * k + pl2;
       double2 ub2[3], gr[3], gs[3], gt[3];
+      const double drf0 = CT(CT_DRF), drf1 = CT(CT_DRF + 1), dsf0 = CT(CT_DSF), dsf1 = CT(CT_DSF + 1);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const double* __restrict__ Uc = p.ub[c] + ebase + 64 * k;
         ub2[c] = __ldg(reinterpret_cast<const double2*>(Uc + pl2));
         const double s0 = __ldg(Uc + sA0), s1 = __ldg(Uc + sA1);
         gr[c] = make_double2(0.0, 0.0);
-        dmma(gr[c], ub2[c].x, DrF[0]);
-        dmma(gr[c], ub2[c].y, DrF[1]);
+        dmma(gr[c], ub2[c].x, drf0);
+        dmma(gr[c], ub2[c].y, drf1);
         gs[c] = make_double2(0.0, 0.0);
-        dmma(gs[c], DsF[0], s0);
-        dmma(gs[c], DsF[1], s1);
+        dmma(gs[c], dsf0, s0);
+        dmma(gs[c], dsf1, s1);
         gt[c] = *reinterpret_cast<const double2*>(Wt + c * N + wt_off(2 * q, g, k));
       }
 
@@ -452,7 +446,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       if (pi == 0 && wid == 0 && it + 1 < n_my) {   // L2 prefetch of the slot's next base-flow element
         int en;
         if constexpr (LIST) en = e_nxt;
-        else if constexpr (XS) en = xs_elem(it + 1);
+        else if constexpr (XS) en = e + 1;
         else en = g0 + (it + 1) * nslots;
         if (elect_one()) {
 #pragma unroll
@@ -465,7 +459,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         auto sel = [h](const double2& x) { return h ? x.y : x.x; };
-        const double w3 = (h ? wij1 : wij0) * wk;
+        const double w3 = CT(CT_WIJ + h) * wk;
         const double pv0 = sel(v0), pv1 = sel(v1), pv2 = sel(v2);
         const double b0 = sel(ub2[0]), b1 = sel(ub2[1]), b2 = sel(ub2[2]);
         double Gp[9];
@@ -544,19 +538,37 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
         *reinterpret_cast<double2*>(scr + c * PLANE + scr_w) = Fs[c];
       }
       __syncwarp();
+      const double drb0 = CT(CT_DRB), drb1 = CT(CT_DRB + 1), dsb0 = CT(CT_DSB), dsb1 = CT(CT_DSB + 1);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         double2 acc = fpw[c];
-        dmma(acc, Fr[c].x, DrB[0]);                        // transposed r: A = own flux pair
-        dmma(acc, Fr[c].y, DrB[1]);
+        dmma(acc, Fr[c].x, drb0);                          // transposed r: A = own flux pair
+        dmma(acc, Fr[c].y, drb1);
         const double t0 = scr[c * PLANE + scr_r0], t1 = scr[c * PLANE + scr_r1];
-        dmma(acc, DsB[0], t0);                             // transposed s
-        dmma(acc, DsB[1], t1);
+        dmma(acc, dsb0, t0);                               // transposed s
+        dmma(acc, dsb1, t1);
         cacc[pi][c] = acc;
       }
       __syncwarp();   // scratch is reused by the next plane
     }
     named_bar_sync(bar_id, C::NSLOT_THR);
+
+    // ---- x stage: fetch the previous element's i = 7 values now (L2 hits, ~1 us under load), use them in the
+    //      final store phase: the latency hides behind the transposed t contraction and its barrier
+    [[maybe_unused]] double pv[NPL][3];
+    [[maybe_unused]] bool xdo[NPL];
+    if constexpr (XS == 2) {
+#pragma unroll
+      for (int pi = 0; pi < NPL; pi++) {
+        const int k = wid + pi * NW;
+        xdo[pi] = xlinked && q == 0 && g >= 1 && g <= 6 && k >= 1 && k <= 6;
+        if (xdo[pi]) {
+          const size_t xoff = ebase - N + 64 * k + 8 * g + 7;        // (i = 7, j = g, k) of the slot's previous element
+#pragma unroll
+          for (int c = 0; c < 3; c++) pv[pi][c] = __ldcg(p.f[c] + xoff);
+        }
+      }
+    }
 
     // ---- transposed t contraction per (component, j) slab, in place in Wt ------------------------------
 #pragma unroll
@@ -565,8 +577,8 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       const int c = task >> 3, j = task & 7;
       const double b0 = Wt[c * N + wt_off(g, j, q)], b1 = Wt[c * N + wt_off(g, j, q + 4)];
       double2 acc = make_double2(0.0, 0.0);
-      dmma(acc, DsB[0], b0);
-      dmma(acc, DsB[1], b1);
+      dmma(acc, CT(CT_DSB), b0);
+      dmma(acc, CT(CT_DSB + 1), b1);
       __syncwarp();
       *reinterpret_cast<double2*>(Wt + c * N + wt_off(2 * q, j, g)) = acc;
     }
@@ -576,36 +588,14 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
 #pragma unroll
     for (int pi = 0; pi < NPL; pi++) {
       const int k = wid + pi * NW;
-      [[maybe_unused]] double pv[3];
-      [[maybe_unused]] bool xdo = false;
-      [[maybe_unused]] size_t xoff = 0;
-      if constexpr (XS == 2) {
-        xdo = xlinked && q == 0 && g >= 1 && g <= 6 && k >= 1 && k <= 6;
-        xoff = ebase - N + 64 * k + 8 * g + 7;          // (i = 7, j = g, k) of the slot's previous element
-        if (xdo) {
-#pragma unroll
-          for (int c = 0; c < 3; c++) pv[c] = __ldcg(p.f[c] + xoff);
-        }
-      }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const double2 rt = *reinterpret_cast<const double2*>(Wt + c * N + wt_off(2 * q, g, k));
         double2 o;
         o.x = cacc[pi][c].x + rt.x;
         o.y = cacc[pi][c].y + rt.y;
-        if constexpr (XS == 1) {
-          // lanes (g,0) and (g,3) swap: this element's i = 0 value against the previous element's i = 7 value
-          double* slot7 = x7 + c * 64 + k * 8 + g;
-          const double mine = (q == 3) ? *slot7 : o.x;
-          const double other = __shfl_xor_sync(0xffffffffu, mine, 3);
-          if (xlinked && g >= 1 && g <= 6 && k >= 1 && k <= 6) {
-            if (q == 0) o.x += other;
-            if (q == 3) p.f[c][ebase - N + 64 * k + 8 * g + 7] = mine + other;
-          }
-          if (q == 3) *slot7 = o.y;
-        }
         if constexpr (XS == 2) {
-          if (xdo) { o.x += pv[c]; p.f[c][xoff] = o.x; }
+          if (xdo[pi]) { o.x += pv[pi][c]; p.f[c][ebase - N + 64 * k + 8 * g + 7] = o.x; }
         }
         *reinterpret_cast<double2*>(p.f[c] + ebase + 64 * k + pl2) = o;
       }
@@ -623,6 +613,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     }
   }
   if constexpr (GS) gs_sum_upto(n_my);
+#undef CT
 }
 
 }  // namespace b200

@@ -148,8 +148,6 @@ struct Handle {
   int xs_enable = 1;               // B200_XSTAGE=0 switches it off
   bool xs_valid = false;
   int xs_nslots = 0;               // element slots of the grid the links were built for
-  int xs_shift = 3;                // runs of 2^xs_shift consecutive elements per slot and window (B200_XS_RUN)
-  int xs_variant = 2;              // B200_XS_VARIANT: 1 = shfl + shared memory, 2 = re-load from L2
   int xs_nolink = 0;               // B200_XS_NOLINK=1 (diagnostic): same element map, no class summed in the kernel
   unsigned char* xs_link = nullptr;
   int *xs_off = nullptr, *xs_dof = nullptr;
@@ -324,7 +322,6 @@ int fill_params2_lx8(Handle* h, const LaunchArgs& a, KParams2<8>& p) {
     if (!h->xs_valid || a.elem_begin != 0 || a.nelem != h->nelv || a.elem_list)
       return fail(B200_ERR_STATE, "internal: x stage without matching link flags");
     p.xlink = h->xs_link;
-    p.xs_shift = h->xs_shift;
   }
   if (a.gs_in_kernel) {
     if (!h->sched_valid || a.elem_begin != 0 || a.nelem != h->sched_nelem)
@@ -356,7 +353,7 @@ int launch_v3_cfg2(Handle* h, const LaunchArgs& a) {
   using C = V3Cfg<NE, NW, DS, NF>;
   if (a.gs_in_kernel != GS) return fail(B200_ERR_STATE, "internal: v3 kernel variant / gs_in_kernel mismatch");
   if (a.xstage != (XS != 0)) return fail(B200_ERR_STATE, "internal: v3 kernel variant / x stage mismatch");
-  constexpr int SMEM = (XS == 1) ? C::SMEM_XS : C::SMEM;
+  constexpr int SMEM = C::SMEM;
   static_assert(SMEM <= 227 * 1024, "v3 configuration exceeds the shared memory of an SM");
   static_assert(C::NTHREADS <= 1024, "v3 configuration exceeds 1024 threads");
   static_assert(C::NTHREADS * MAXREG <= 65536, "v3 configuration exceeds the register file");
@@ -396,10 +393,6 @@ int launch_v3_default(Handle* h, const LaunchArgs& a) {
   const bool full = a.fs[0] || a.fin[0];
   if (a.xstage) {
     if (a.gs_in_kernel || a.elem_list) return fail(B200_ERR_STATE, "internal: x stage with in-kernel gs / element list");
-    if (h->xs_variant == 1) {
-      if (full) return launch_v3_cfg2<XS_NE, 4, 1, NF_FULL, 168, false, false, false, 1>(h, a);
-      return launch_v3_cfg2<XS_NE, 4, 2, NF_FUSED, 168, false, false, false, 1>(h, a);
-    }
     if (full) return launch_v3_cfg2<XS_NE, 4, 1, NF_FULL, 168, false, false, false, 2>(h, a);
     return launch_v3_cfg2<XS_NE, 4, 2, NF_FUSED, 168, false, false, false, 2>(h, a);
   }
@@ -553,7 +546,13 @@ int gs_step_pass(Handle* h, double* f0, double* f1, double* f2, bool xs) {
   const int nc = xs ? h->xs_nclass : h->nclass;
   if (nc == 0) return B200_OK;
   const int threads = 256, grid = grid_for(nc, threads, h->num_sm, 3);
-  if (xs)
+  if (xs && h->gs_un == 2)
+    gs_op_kernel<3, 2, 2><<<grid_for(nc, threads, h->num_sm, 2), threads, 0, h->stream>>>(f0, f1, f2, h->xs_off, h->xs_dof, nc, h->xs_skip);
+  else if (xs && h->gs_un == 4)
+    gs_op_kernel<3, 4, 2><<<grid_for(nc, threads, h->num_sm, 2), threads, 0, h->stream>>>(f0, f1, f2, h->xs_off, h->xs_dof, nc, h->xs_skip);
+  else if (xs && h->gs_un == 8)
+    gs_op_kernel<3, 1, 3><<<grid_for(nc, threads, h->num_sm, 8), threads, 0, h->stream>>>(f0, f1, f2, h->xs_off, h->xs_dof, nc, h->xs_skip);
+  else if (xs)
     gs_op_kernel<3, 1, 3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->xs_off, h->xs_dof, nc, h->xs_skip);
   else
     gs_op_kernel<3, 1, 3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof, nc, h->gs_skip);
@@ -756,12 +755,12 @@ int build_xstage(Handle* h) {
   CK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (size_t)ne, st));
   const int gc = grid_for(nc, threads, h->num_sm, 8);
   if (!h->xs_nolink) {
-    xs_candidate_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, h->xs_shift, d_cnt);
+    xs_candidate_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, d_cnt);
     LAUNCHED();
   }
   xs_link_kernel<<<grid_for(ne, threads, h->num_sm, 8), threads, 0, st>>>(d_cnt, ne, h->xs_link);
   LAUNCHED();
-  xs_keep_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, h->xs_shift, h->xs_link, d_keep, d_mem);
+  xs_keep_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, h->xs_link, d_keep, d_mem);
   LAUNCHED();
   CK(cudaGetLastError());
   void* d_tmp = nullptr;
@@ -944,14 +943,6 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   if (g) h->gs_l2hint = atoi(g) != 0;
   g = getenv("B200_XSTAGE");
   if (g) h->xs_enable = atoi(g) != 0;
-  g = getenv("B200_XS_RUN");       // run length (rounded down to a power of two; 0: one contiguous run per slot)
-  if (g) {
-    const int r = atoi(g);
-    h->xs_shift = 30;
-    if (r > 0) { h->xs_shift = 0; while ((2 << h->xs_shift) <= r && h->xs_shift < 30) h->xs_shift++; }
-  }
-  g = getenv("B200_XS_VARIANT");
-  if (g) h->xs_variant = atoi(g) == 1 ? 1 : 2;
   g = getenv("B200_XS_NOLINK");
   if (g) h->xs_nolink = atoi(g) != 0;
   *handle = h;
@@ -1464,8 +1455,10 @@ int b200_sensitivity(void* sens, const void* u, const void* v, const void* w, co
 }
 
 int b200_steady_field_update(double* result, const void* x, void* x_old, const int* n, void* stream) {
-  if (!result || !x || !x_old || !n) return fail(B200_ERR_ARG, "steady_field_update: null argument");
+  if (!result || !n) return fail(B200_ERR_ARG, "steady_field_update: null argument");
   if (*n < 0) return fail(B200_ERR_ARG, "steady_field_update: n=%d", *n);
+  if (*n == 0) { *result = 0.0; return B200_OK; }      // a rank without elements
+  if (!x || !x_old) return fail(B200_ERR_ARG, "steady_field_update: null field");
   // per-device scratch (partials + result), allocated once: the call runs every time step
   static double* scratch[64] = {};
   int dev = 0;
@@ -1506,7 +1499,7 @@ static int deriv_run(Handle* h, int mode, const void* u1, const void* u2, const 
 // deterministic local dot product on the handle's stream (synchronises: returns a host scalar)
 static int dot_local(Handle* h, const double* a, const double* b, const int* mask, int mask_size, double* result) {
   const int nblk = 1024;
-  if (!h->d_partial) if (int r = dmalloc(&h->d_partial, (size_t)nblk)) return r;
+  if (!h->d_partial) if (int r = dmalloc(&h->d_partial, (size_t)nblk + 64)) return r;
   const int64_t count = mask ? (int64_t)mask_size : h->n;
   dot_partial_kernel<<<nblk, 256, 0, h->stream>>>(a, b, mask, count, h->d_partial);
   LAUNCHED();
@@ -1623,32 +1616,26 @@ static int helm_run(Handle* h, int mode, const double* u, const double* jacinv, 
   return B200_OK;
 }
 
-// glsc3(a, mult, b): deterministic local sum, then the sum over ranks (Neko: MPI_Allreduce; here NCCL)
-static int glsc3_global(Handle* h, const double* a, const double* m, const double* b, double* result) {
+// glsc3(a, mult, b) into the device state: deterministic block partials, fixed-tree sum, sum over the ranks
+// (Neko: MPI_Allreduce; here ncclAllReduce on the device scalar), then the scalar recurrence of `step`
+static int cg_dot_step(Handle* h, const double* a, const double* m, const double* b, CgState* st, int step, int it,
+                       double nf, double tol) {
   const int nblk = 1024;
-  if (!h->d_partial) if (int r = dmalloc(&h->d_partial, (size_t)nblk)) return r;
   dot3_partial_kernel<<<nblk, 256, 0, h->stream>>>(a, m, b, h->n, h->d_partial);
   LAUNCHED();
+  cg_sum_kernel<<<1, 256, 0, h->stream>>>(h->d_partial, nblk, st);
+  LAUNCHED();
+  if (h->comm && h->nranks > 1) NK(ncclAllReduce(&st->tmp, &st->tmp, 1, ncclDouble, ncclSum, h->comm, h->stream));
+  cg_step_kernel<<<1, 32, 0, h->stream>>>(st, step, it, nf, tol);
+  LAUNCHED();
   CK(cudaGetLastError());
-  std::vector<double> part(nblk);
-  CK(cudaMemcpyAsync(part.data(), h->d_partial, sizeof(double) * nblk, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  double s = 0.0;
-  for (double v : part) s += v;
-  if (h->comm && h->nranks > 1) {
-    CK(cudaMemcpyAsync(h->d_partial, &s, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    NK(ncclAllReduce(h->d_partial, h->d_partial, 1, ncclDouble, ncclSum, h->comm, h->stream));
-    CK(cudaMemcpyAsync(&s, h->d_partial, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
-  *result = s;
   return B200_OK;
 }
 
 int b200_pde_filter_apply(void* handle, void* x_out, const void* x_in, const void* jacinv, const void* mult,
                           const double* radius, const double* abs_tol, const int* max_iter,
-                          const int* precond, const double* norm_fac, int* iters, double* res_start,
-                          double* res_final) {
+                          const int* precond, const double* norm_fac, const int* x0_is_input, int* iters,
+                          double* res_start, double* res_final) {
   if (!handle) return fail(B200_ERR_ARG, "null handle");
   Handle* h = H(handle);
   if (!x_out || !x_in || !jacinv || !mult || !radius || !abs_tol || !max_iter)
@@ -1656,61 +1643,76 @@ int b200_pde_filter_apply(void* handle, void* x_out, const void* x_in, const voi
   if (!h->have_space || !h->have_geom) return fail(B200_ERR_STATE, "set_space/set_geometry not called");
   if (!h->have_gs) return fail(B200_ERR_STATE, "pde_filter_apply: b200_gs_init not called");
   CK(cudaSetDevice(h->device));
-  NvtxRange nvtx("PDE filter solve (b200_pde_filter_apply)");
+  NvtxRange nvtx("filter solve (b200_pde_filter_apply)");     // the reference's region name, PDE_filter_mapping.f90:255
   const int64_t n = h->n;
   if (!h->work6 && n > 0) if (int r = dmalloc(&h->work6, 6 * (size_t)n)) return r;
+  if (!h->d_partial) if (int r = dmalloc(&h->d_partial, (size_t)1024 + 64)) return r;
+  CgState* st = reinterpret_cast<CgState*>(h->d_partial + 1024);
   double *rr = h->work6, *pp = rr + n, *zz = pp + n, *ww = zz + n, *dinv = ww + n;
   double* x = (double*)x_out;
   const double* mlt = (const double*)mult;
   const double h1 = (*radius) * (*radius), h2 = 1.0;          // PDE_filter_mapping.f90:229-231 / :240-244
   const double nf = norm_fac ? *norm_fac : 1.0;
   const bool jacobi = !precond || *precond != 0;
+  const bool x0 = x0_is_input && *x0_is_input != 0;
   const int threads = 256;
   const int grid = grid_for(n, threads, h->num_sm, 8);
-  cudaStream_t st = h->stream;
+  cudaStream_t sm = h->stream;
   // RHS = B * X_in, direct-stiffness summed (:231,251)
-  cg_col3_kernel<<<grid, threads, 0, st>>>(rr, (const double*)x_in, h->B, n);
+  cg_col3_kernel<<<grid, threads, 0, sm>>>(rr, (const double*)x_in, h->B, n);
   LAUNCHED();
   if (int r = b200_gs_op(handle, rr)) return r;
-  // Neko's Krylov solvers start from x = 0 (the field_copy at :248 is overwritten by the solver)
-  CK(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, st));
-  CK(cudaMemsetAsync(pp, 0, sizeof(double) * (size_t)n, st));
+  CK(cudaMemsetAsync(pp, 0, sizeof(double) * (size_t)n, sm));
+  if (x0) {
+    // "copy the unfiltered design as an initial guess" (:246-248): x = X_in, r = b - A x
+    if (x != (const double*)x_in) CK(cudaMemcpyAsync(x, x_in, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, sm));
+    if (int r = helm_run(h, 0, x, (const double*)jacinv, ww, h1, h2)) return r;
+    if (int r = b200_gs_op(handle, ww)) return r;
+    cg_sub_kernel<<<grid, threads, 0, sm>>>(rr, ww, n);
+    LAUNCHED();
+  } else {
+    // Neko's Krylov solvers zero x on entry (the field_copy at :248 is then overwritten)
+    CK(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)n, sm));
+  }
   if (jacobi) {
     if (int r = helm_run(h, 1, nullptr, (const double*)jacinv, dinv, h1, h2)) return r;
     if (int r = b200_gs_op(handle, dinv)) return r;
-    cg_invert_kernel<<<grid, threads, 0, st>>>(dinv, n);
+    cg_invert_kernel<<<grid, threads, 0, sm>>>(dinv, n);
     LAUNCHED();
   }
-  double rtz1 = 1.0, rtz2, rtr = 0.0;
-  if (int r = glsc3_global(h, rr, mlt, rr, &rtr)) return r;
-  double rnorm = sqrt(rtr) * nf;
-  if (res_start) *res_start = rnorm;
+  if (int r = cg_dot_step(h, rr, mlt, rr, st, CG_INIT, 0, nf, *abs_tol)) return r;
+  CgState hs;
+  memset(&hs, 0, sizeof hs);
+  const int CHUNK = 8;                    // iterations enqueued between two looks at the state
   int it = 0;
-  for (it = 1; it <= *max_iter && rnorm >= *abs_tol; it++) {
-    const double* z = rr;
-    if (jacobi) {
-      cg_col3_kernel<<<grid, threads, 0, st>>>(zz, rr, dinv, n);
+  while (true) {
+    CK(cudaMemcpyAsync(&hs, st, sizeof hs, cudaMemcpyDeviceToHost, sm));
+    CK(cudaStreamSynchronize(sm));
+    if (hs.done || it >= *max_iter) break;
+    const int upto = std::min(*max_iter, it + CHUNK);
+    for (it = it + 1; it <= upto; it++) {
+      const double* z = rr;
+      if (jacobi) {
+        cg_col3_kernel<<<grid, threads, 0, sm>>>(zz, rr, dinv, n);
+        LAUNCHED();
+        z = zz;
+      }
+      if (int r = cg_dot_step(h, rr, mlt, z, st, CG_RTZ, it, nf, *abs_tol)) return r;
+      cg_p_update_kernel<<<grid, threads, 0, sm>>>(pp, z, st, n);
       LAUNCHED();
-      z = zz;
+      if (int r = helm_run(h, 0, pp, (const double*)jacinv, ww, h1, h2)) return r;
+      if (int r = b200_gs_op(handle, ww)) return r;
+      if (int r = cg_dot_step(h, ww, mlt, pp, st, CG_PAP, it, nf, *abs_tol)) return r;
+      cg_xr_update_kernel<<<grid, threads, 0, sm>>>(x, rr, pp, ww, st, n);
+      LAUNCHED();
+      if (int r = cg_dot_step(h, rr, mlt, rr, st, CG_RTR, it, nf, *abs_tol)) return r;
     }
-    rtz2 = rtz1;
-    if (int r = glsc3_global(h, rr, mlt, z, &rtz1)) return r;
-    const double beta = (it == 1) ? 0.0 : rtz1 / rtz2;
-    cg_p_update_kernel<<<grid, threads, 0, st>>>(pp, z, beta, n);
-    LAUNCHED();
-    if (int r = helm_run(h, 0, pp, (const double*)jacinv, ww, h1, h2)) return r;
-    if (int r = b200_gs_op(handle, ww)) return r;
-    double pap = 0.0;
-    if (int r = glsc3_global(h, ww, mlt, pp, &pap)) return r;
-    const double alpha = rtz1 / pap;
-    cg_xr_update_kernel<<<grid, threads, 0, st>>>(x, rr, pp, ww, alpha, n);
-    LAUNCHED();
-    if (int r = glsc3_global(h, rr, mlt, rr, &rtr)) return r;
-    rnorm = sqrt(rtr) * nf;
+    it = upto;
   }
   CK(cudaGetLastError());
-  if (iters) *iters = it - 1;
-  if (res_final) *res_final = rnorm;
+  if (iters) *iters = hs.iters;
+  if (res_start) *res_start = hs.res_start;
+  if (res_final) *res_final = hs.rnorm;
   return B200_OK;
 }
 

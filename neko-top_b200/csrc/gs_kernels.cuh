@@ -12,7 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "adjrhs_kernel_v3.cuh"   // xs_map / xs_is_run_start: the element -> slot map of the x-stage kernels
+#include "adjrhs_kernel_v3.cuh"   // xs_run_begin / xs_is_run_start: the element -> slot map of the x-stage kernels
 
 namespace b200 {
 
@@ -377,10 +377,10 @@ __global__ void __launch_bounds__(256) gs_wide_kernel(double* __restrict__ f0, d
 //                        slot's run, counts one for element e;
 //   xs_link_kernel:      xlink[e] = all 36 classes of the face were found;
 //   xs_keep_kernel:      a class stays in the gather-scatter pass unless it is such a pair of a linked element.
-// Runs: xs_map / xs_is_run_start in adjrhs_kernel_v3.cuh (windows of nslots runs of 2^shift elements + a balanced tail).
+// Runs: xs_run_begin / xs_is_run_start in adjrhs_kernel_v3.cuh (one contiguous run of elements per slot).
 // returns the later element of the pair if class c matches the pattern, else -1
 __device__ __forceinline__ int xs_pair_elem(const int* __restrict__ off, const int* __restrict__ dof, int c,
-                                            int nelem, int nslots, int shift) {
+                                            int nelem, int nslots) {
   const int b = off[c];
   if (off[c + 1] - b != 2) return -1;
   const int d0 = dof[b], d1 = dof[b + 1];
@@ -390,14 +390,14 @@ __device__ __forceinline__ int xs_pair_elem(const int* __restrict__ off, const i
   if ((l0 & 7) != 7 || (l1 & 7) != 0 || (l0 >> 3) != (l1 >> 3)) return -1;
   const int j = (l0 >> 3) & 7, k = l0 >> 6;
   if (j < 1 || j > 6 || k < 1 || k > 6) return -1;
-  if (xs_is_run_start(e1, nelem, nslots, shift)) return -1;
+  if (xs_is_run_start(e1, nelem, nslots)) return -1;
   return e1;
 }
 __global__ void xs_candidate_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass,
-                                    int nelem, int nslots, int shift, int* __restrict__ cnt) {
+                                    int nelem, int nslots, int* __restrict__ cnt) {
   const int stride = gridDim.x * blockDim.x;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
-    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots, shift);
+    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots);
     if (e1 >= 0) atomicAdd(cnt + e1, 1);
   }
 }
@@ -407,11 +407,11 @@ __global__ void xs_link_kernel(const int* __restrict__ cnt, int nelem, unsigned 
 }
 // keep[c] = 1 / members[c] = class size if the class stays in the pass, else 0 / 0
 __global__ void xs_keep_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass, int nelem,
-                               int nslots, int shift, const unsigned char* __restrict__ xlink, int* __restrict__ keep,
+                               int nslots, const unsigned char* __restrict__ xlink, int* __restrict__ keep,
                                int* __restrict__ members) {
   const int stride = gridDim.x * blockDim.x;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
-    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots, shift);
+    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots);
     const bool k = !(e1 >= 0 && xlink[e1]);
     keep[c] = k ? 1 : 0;
     members[c] = k ? off[c + 1] - off[c] : 0;

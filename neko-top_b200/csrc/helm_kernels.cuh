@@ -123,7 +123,57 @@ static __global__ void __launch_bounds__(256) dot3_partial_kernel(const double* 
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
-// small vector updates of the CG iteration
+// ---- preconditioned CG with every scalar on the device --------------------------------------------------------
+// The iteration is enqueued without host synchronisation: inner products are deterministic block partials
+// (dot3_partial_kernel) summed in a fixed tree by cg_sum_kernel, the scalar recurrences run in cg_step_kernel, and
+// the vector updates read alpha / beta from the state.  Once the residual is below the tolerance `done` is set and
+// every later kernel of the chunk is a no-op, so the result is exactly that of a loop that stops at that
+// iteration (Neko cg_t: `if (rnorm .lt. abs_tol) exit`).
+struct CgState {
+  double rtz1, rtz2, pap, rtr, rnorm, res_start, alpha, beta, tmp;
+  int done, iters;
+};
+static __global__ void __launch_bounds__(256) cg_sum_kernel(const double* __restrict__ partial, int nblk,
+                                                           CgState* __restrict__ st) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 256) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st->tmp = sh[0];
+}
+enum : int { CG_INIT = 0, CG_RTZ = 1, CG_PAP = 2, CG_RTR = 3 };
+static __global__ void cg_step_kernel(CgState* __restrict__ st, int step, int it, double norm_fac, double abs_tol) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double v = st->tmp;
+  if (step == CG_INIT) {
+    st->rtr = v;
+    st->rnorm = sqrt(v) * norm_fac;
+    st->res_start = st->rnorm;
+    st->rtz1 = 1.0; st->rtz2 = 1.0; st->alpha = 0.0; st->beta = 0.0; st->pap = 0.0;
+    st->iters = 0;
+    st->done = (st->rnorm < abs_tol) ? 1 : 0;
+    return;
+  }
+  if (st->done) return;
+  if (step == CG_RTZ) {
+    st->rtz2 = st->rtz1;
+    st->rtz1 = v;
+    st->beta = (it == 1) ? 0.0 : st->rtz1 / st->rtz2;
+  } else if (step == CG_PAP) {
+    st->pap = v;
+    st->alpha = st->rtz1 / v;
+  } else {
+    st->rtr = v;
+    st->rnorm = sqrt(v) * norm_fac;
+    st->iters = it;
+    if (st->rnorm < abs_tol) st->done = 1;
+  }
+}
 static __global__ void cg_col3_kernel(double* __restrict__ out, const double* __restrict__ a,
                                       const double* __restrict__ b, int64_t n) {   // out = a*b
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -133,14 +183,22 @@ static __global__ void cg_invert_kernel(double* __restrict__ a, int64_t n) {    
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = 1.0 / a[i];
 }
-static __global__ void cg_p_update_kernel(double* __restrict__ p, const double* __restrict__ z, double beta,
-                                          int64_t n) {                              // p = beta*p + z (add2s1)
+static __global__ void cg_sub_kernel(double* __restrict__ r, const double* __restrict__ w, int64_t n) {   // r -= w
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) r[i] = r[i] - w[i];
+}
+static __global__ void cg_p_update_kernel(double* __restrict__ p, const double* __restrict__ z,
+                                          const CgState* __restrict__ st, int64_t n) {   // p = beta*p + z (add2s1)
+  if (st->done) return;
+  const double beta = st->beta;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = beta * p[i] + z[i];
 }
 static __global__ void cg_xr_update_kernel(double* __restrict__ x, double* __restrict__ r,
                                            const double* __restrict__ p, const double* __restrict__ w,
-                                           double alpha, int64_t n) {               // x += alpha p ; r -= alpha w
+                                           const CgState* __restrict__ st, int64_t n) {  // x += alpha p ; r -= alpha w
+  if (st->done) return;
+  const double alpha = st->alpha;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     x[i] = x[i] + alpha * p[i];

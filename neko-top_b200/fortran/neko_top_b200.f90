@@ -214,12 +214,13 @@ module neko_top_b200
 
      integer(c_int) function b200_pde_filter_apply(handle, x_out_d, x_in_d, &
           jacinv_d, mult_d, radius, abs_tol, max_iter, precond, norm_fac, &
-          iters, res_start, res_final) bind(c, name='b200_pde_filter_apply')
+          x0_is_input, iters, res_start, res_final) &
+          bind(c, name='b200_pde_filter_apply')
        use, intrinsic :: iso_c_binding
        type(c_ptr), value :: handle
        type(c_ptr), value :: x_out_d, x_in_d, jacinv_d, mult_d
        real(c_double) :: radius, abs_tol, norm_fac
-       integer(c_int) :: max_iter, precond, iters
+       integer(c_int) :: max_iter, precond, x0_is_input, iters
        real(c_double) :: res_start, res_final
      end function b200_pde_filter_apply
 

@@ -295,9 +295,14 @@ def mask_exterior_const(fld, mask, const):
 class PDE_filter_t:
     """mapping_functions/PDE_filter_mapping.f90:52-363: apply_forward / apply_backward = one Helmholtz solve."""
 
-    def __init__(self, handle, coef, mult, r, abs_tol=1e-10, max_iter=800, precond="jacobi", norm_fac=1.0):
+    def __init__(self, handle, coef, mult, r=0.01, abs_tol=1e-10, max_iter=200, precond="ident", norm_fac=1.0,
+                 x0_is_input=False):
+        """Defaults = the reference's hard-coded attributes (PDE_filter_mapping.f90:131-137: r = 0.01,
+        abstol 1e-10, 200 iterations, "ident" preconditioner).  x0_is_input: start the Krylov iteration from the
+        unfiltered field (the intent of :246-248) instead of from zero (what Neko's solvers do on entry)."""
         self.handle, self.coef, self.mult = handle, coef, mult
         self.r, self.abs_tol, self.max_iter, self.precond, self.norm_fac = r, abs_tol, max_iter, precond, norm_fac
+        self.x0_is_input = bool(x0_is_input)
         self.ksp_results = None
 
     def _solve(self, X_out, X_in):
@@ -305,7 +310,7 @@ class PDE_filter_t:
         check(_lib.lib().b200_pde_filter_apply(self.handle.handle.h, _ptr(X_out), _ptr(X_in), _ptr(self.coef.jacinv),
                                                _ptr(self.mult), _cd(self.r), _cd(self.abs_tol), _ci(self.max_iter),
                                                _ci(0 if self.precond == "ident" else 1), _cd(self.norm_fac),
-                                               C.byref(it), C.byref(r0), C.byref(r1)))
+                                               _ci(self.x0_is_input), C.byref(it), C.byref(r0), C.byref(r1)))
         self.ksp_results = (it.value, r0.value, r1.value)
 
     def apply_forward(self, X_out, X_in):

@@ -330,7 +330,7 @@ def test_config1_full_size_vs_oracle(oracle):
     f, sens = [_nan(n) for _ in range(3)], _nan(n)
     op.step(v, ub, f, rho=rho, sens=sens)
     active, nlinked, _, _ = op.xstage_info()
-    assert active and nlinked > 0.9 * brick.nelv * (ne - 1) / ne
+    assert active and nlinked > 0.85 * brick.nelv * (ne - 1) / ne
     c = lambda t: t.cpu().numpy()
     fo, so, _ = oracle.adjoint_rhs([c(a) for a in v], [c(a) for a in ub], lx, brick.nelv, sp.dx, sp.wx,
                                    [c(g) for g in Gf], c(Bf), rho=c(rho))

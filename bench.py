@@ -381,11 +381,14 @@ def run_b200(args):
         torch.cuda.synchronize()
         dt = maxr(time.perf_counter() - t0)
         barrier()
-        e2e_ok = all(bool(torch.equal(hf[c], f[c].cpu())) for c in range(3)) and bool(torch.equal(hs, sens.cpu()))
+        # the host-buffer path sums every class from its member list; the device path's staged sums associate 4- and
+        # 8-member classes pairwise: equal up to rounding
+        e2e_diff = max(float((hf[c] - f[c].cpu()).abs().max() / f[c].abs().max().cpu()) for c in range(3))
+        e2e_ok = e2e_diff <= 4e-15 and bool(torch.equal(hs, sens.cpu()))
         e2e = {"value": n_global / (dt / args.e2e_steps) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(7 * n * 8), "d2h_bytes_per_step": int(4 * n * 8),
                "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-               "matches_device_path": bool(e2e_ok),
+               "matches_device_path": bool(e2e_ok), "max_rel_diff_vs_device_path": e2e_diff,
                "note": "b200_adjrhs_step_host: 7 input fields H2D from pinned memory, f(3)+sens D2H, "
                        "geometry resident (set once like coef_t); bytes are per rank"}
         del hv, hub, hrho, hf, hs
@@ -408,8 +411,8 @@ def run_b200(args):
             traffic = None
     xs_active, xs_linked, xs_left, xs_total = op.xstage_info()
     if lx == 8:
-        kname = ("adjrhs_v3_kernel<3,4,2,14,168,XS> (fused element kernel, DMMA contractions, i-face pair classes "
-                 "summed in registers; 168 B/DOF algorithmic)") if xs_active else \
+        kname = ("adjrhs_v3_kernel<3,4,2,14,168,XS> (fused element kernel, DMMA contractions, x-face node pairs "
+                 "summed in the kernel; 168 B/DOF algorithmic)") if xs_active else \
                 "adjrhs_v3_kernel<3,4,2,14,168> (fused element kernel, DMMA contractions; 168 B/DOF algorithmic)"
     else:
         kname = "adjrhs_v2_kernel (fused element kernel; 168 B/DOF algorithmic)"
@@ -418,7 +421,7 @@ def run_b200(args):
                 "traffic_source": ("profiles/traffic.json (ncu --set full capture of this kernel at this size; not "
                                    "re-measured in this run)") if traffic is not None else None,
                 "kernel": kname,
-                "gs_classes_in_pass": int(xs_left), "gs_classes_total": int(xs_total),
+                "gs_stage_level": int(xs_active), "gs_classes_in_pass": int(xs_left), "gs_classes_total": int(xs_total),
                 "kernel_ms": elem_ms, "gs_ms": gs_ms, "algorithmic_bytes_per_launch": n * bpd,
                 "peak_source": peak_src,
                 "step_GBps": n * sem.algorithmic_bytes_per_dof(lx, True) / (ms_step * 1e-3) / 1e9}

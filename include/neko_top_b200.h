@@ -293,17 +293,25 @@ int b200_adjrhs_set_gs_fused(void* handle, const int* flag);
 /* *fused = 1 if b200_adjrhs_step currently sums node classes inside the element kernel;
  * *classes_in_kernel of *classes_total are handled there (the rest: shared-node path, > 16 members). */
 int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, int64_t* classes_total);
-/* "x stage" of the lx = 8 element kernel (default on; environment B200_XSTAGE=0 or *flag = 0 switches it off).
- * In b200_adjrhs_step every element slot walks a contiguous run of elements; where consecutive elements e-1, e
- * are glued i = lx-1 -> i = 0 node by node (verified against the classes of b200_gs_init) the kernel sums the
- * face-interior pair classes in registers, and the gather-scatter pass that follows runs over the remaining
- * classes only -- it then touches 44 % instead of 100 % of the 32-byte sectors of f.  a + b is commutative, so
- * the result stays bit-identical to gs_op(GS_OP_ADD) after the plain kernel (adjoint_pnpn.f90:755-757).
- * Used when the elements are in mesh order (no b200_adjrhs_set_element_order), gs mode 0, no point-zone mask. */
+/* Staged direct-stiffness summation of b200_adjrhs_step at lx = 8 (environment B200_XSTAGE):
+ *   *flag = 0  plain element kernel + gather-scatter pass over all class lists;
+ *   *flag = 1  every element slot walks a contiguous run of elements; where consecutive elements e-1, e are glued
+ *              i = lx-1 -> i = 0 node by node the kernel sums the 2-member classes of that face itself (the
+ *              partner value is re-read from L2) and the pass runs over the remaining classes -- it then touches
+ *              44 % instead of 100 % of the 32-byte sectors of f; bit-identical to flag 0 (a + b commutes);
+ *   *flag = 2  (default) additionally every class that is a PRODUCT of face pairings (face-interior nodes, 2x2
+ *              edges, 2x2x2 vertices of a locally structured mesh) is summed direction by direction: x in the
+ *              kernel, y and z by two face passes over contiguous rows / planes; only irregular and
+ *              partition-boundary classes stay in the class-list pass.  All copies of a node still end with
+ *              identical bits; 4- and 8-member sums are associated pairwise, i.e. they differ from flag 0 by
+ *              rounding (<= 1e-15 relative).
+ * Everything is verified against the classes of b200_gs_init at set-up; nothing is assumed about the mesh
+ * (gs_kernels.cuh "staged").  Used when the elements are in mesh order (no b200_adjrhs_set_element_order), gs
+ * mode 0, no point-zone mask.  Replaces gs_Xh%op(f, GS_OP_ADD) after the RHS (adjoint_pnpn.f90:755-757). */
 int b200_adjrhs_set_xstage(void* handle, const int* flag);
-/* *active = 1 if the last/next b200_adjrhs_step uses it; *linked_elements = elements whose i = 0 face is summed
- * in the kernel; *classes_left of *classes_total stay in the gather-scatter pass */
-int b200_adjrhs_xstage_info(void* handle, int* active, int64_t* linked_elements, int64_t* classes_left,
+/* *active = level used by the last/next b200_adjrhs_step (0, 1, 2); *classes_staged = classes summed by the
+ * kernel / face passes; *classes_left of *classes_total stay in the class-list pass */
+int b200_adjrhs_xstage_info(void* handle, int* active, int64_t* classes_staged, int64_t* classes_left,
                             int64_t* classes_total);
 
 /* ---- diagnostics ----------------------------------------------------------------------------*/

@@ -63,7 +63,7 @@ struct KParams2 {
   unsigned long long* gs_done;  // one counter per window of nslots consecutive positions (zeroed per launch)
   int gs_lag;                 // windows between storing an element and summing its classes (>= 1)
   int elem_base;              // v2: added to every element index (field pointers stay 16-byte aligned for odd LX)
-  const unsigned char* xlink; // v3 XS: xlink[e] != 0: faces (e-1: i=7) and (e: i=0) are glued node by node
+  const unsigned long long* xmask;  // v3 XS: bit (j + 8k) of xmask[e]: nodes (e-1; 7,j,k) and (e; 0,j,k) are summed in the kernel
 };
 
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {

@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(V3Cfg<NE, NW, DS, NF>::NTHREADS, 1) __maxnreg_
 adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   using C = V3Cfg<NE, NW, DS, NF>;
   // XS = 2: lane (g,0) re-loads the previous element's i = 7 value from L2 (__ldcg) and rewrites it -- no cross-lane
-  // traffic (XS = 1, an exchange through shfl + shared memory, measured 5 % slower, is gone)
+  // traffic.  (Tried and dropped, r02c/r02j: the value kept in shared memory or in registers of lane (g,3) and
+  // swapped with shfl.xor(3): 4-5 % slower.)
   static_assert(!XS || (!GS && !LIST), "the x stage runs on contiguous element runs without the in-kernel gs");
   constexpr int LX = 8, N = 512, PLANE = 64;
   constexpr int NPL = LX / NW;        // planes per warp
@@ -380,10 +381,10 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     else if constexpr (XS) e = e_first + it;
     else e = g0 + it * nslots;
     const size_t ebase = (size_t)e * N;
-    // xlink[e] != 0: e's i = 0 face is glued to the i = 7 face of element e-1, and e-1 is the element this slot
-    // processed in its previous iteration (the set-up knows the runs: xs_is_run_start)
-    [[maybe_unused]] bool xlinked = false;
-    if constexpr (XS) xlinked = (__ldg(p.xlink + e) != 0);
+    // xmask[e] bit (j + 8k): node (0,j,k) of e and node (7,j,k) of element e-1 are summed here; e-1 is then the
+    // element this slot processed in its previous iteration (the set-up knows the runs: xs_is_run_start)
+    [[maybe_unused]] unsigned long long xm = 0ull;
+    if constexpr (XS) xm = __ldg(p.xmask + e);
 
     // ---- t-derivatives of the base flow, per (component, j) slab -> Wt --------------------------------
 #pragma unroll
@@ -561,7 +562,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
 #pragma unroll
       for (int pi = 0; pi < NPL; pi++) {
         const int k = wid + pi * NW;
-        xdo[pi] = xlinked && q == 0 && g >= 1 && g <= 6 && k >= 1 && k <= 6;
+        xdo[pi] = q == 0 && ((xm >> (g + 8 * k)) & 1ull);
         if (xdo[pi]) {
           const size_t xoff = ebase - N + 64 * k + 8 * g + 7;        // (i = 7, j = g, k) of the slot's previous element
 #pragma unroll

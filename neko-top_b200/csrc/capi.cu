@@ -145,11 +145,16 @@ struct Handle {
 
   // x stage of the lx = 8 element kernel (adjrhs_kernel_v3.cuh XS): per-element link flags and the CSR lists
   // of the classes that stay in the gather-scatter pass
-  int xs_enable = 1;               // B200_XSTAGE=0 switches it off
+  // staged direct-stiffness summation (gs_kernels.cuh "staged"): 0 off, 1 = x pairs inside the lx = 8 element
+  // kernel (bit-identical to the plain pass), 2 = x in the kernel + y and z face passes (product classes)
+  int xs_enable = 2;               // B200_XSTAGE
   bool xs_valid = false;
+  int xs_level = 0;                // level the lists below were built for
   int xs_nslots = 0;               // element slots of the grid the links were built for
-  int xs_nolink = 0;               // B200_XS_NOLINK=1 (diagnostic): same element map, no class summed in the kernel
-  unsigned char* xs_link = nullptr;
+  int xs_nolink = 0;               // B200_XS_NOLINK=1 (diagnostic): same element map, no class staged
+  unsigned long long* xs_mask[3] = {};   // per element: nodes of the i/j/k = 0 face summed with the neighbour's 7 face
+  int* xs_pred[3] = {};            // neighbour element across that face
+  bool xs_have[3] = {};            // any bit set in direction a
   int *xs_off = nullptr, *xs_dof = nullptr;
   unsigned char* xs_skip = nullptr;
   int xs_nclass = 0;
@@ -321,7 +326,7 @@ int fill_params2_lx8(Handle* h, const LaunchArgs& a, KParams2<8>& p) {
   if (a.xstage) {
     if (!h->xs_valid || a.elem_begin != 0 || a.nelem != h->nelv || a.elem_list)
       return fail(B200_ERR_STATE, "internal: x stage without matching link flags");
-    p.xlink = h->xs_link;
+    p.xmask = h->xs_mask[0];
   }
   if (a.gs_in_kernel) {
     if (!h->sched_valid || a.elem_begin != 0 || a.nelem != h->sched_nelem)
@@ -462,20 +467,14 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
     // lx != 8 (v2): configurations from the r01j sweep (tools/lxsweep.py, profiles/r01j_lxsweep.jsonl).  What
     // matters most is a warp count whose per-scheduler register share avoids spills (the register file is
     // split over four schedulers: 9-12 warps -> 168 registers, <= 8 warps -> 255); cfg 32 = the older choice.
+    // (deeper plane rings -- 3..7 stages -- were measured in r02j: no gain at lx = 5, 6, 9, 10, +6 % at lx = 7 with 7
+    // stages; the consumers' waits on the ring are the single producer lane's issue rate, not the ring depth)
     case 5: return cfg == 32 ? launch_v2<5, 8, 2, 224>(h, a) : launch_v2<5, 11, 2, 168>(h, a);
     case 6: return cfg == 32 ? launch_v2<6, 4, 2, 224>(h, a) : launch_v2<6, 5, 2, 168>(h, a);
-    case 7: return cfg == 32 ? launch_v2<7, 4, 2, 224>(h, a) : launch_v2<7, 3, 4, 255, 3, 2>(h, a);
+    case 7: return cfg == 32 ? launch_v2<7, 4, 2, 224>(h, a) : launch_v2<7, 3, 7, 255, 3, 6>(h, a);
     case 8:
       switch (cfg) {
-        case 1: return launch_v2<8, 4, 2, 224>(h, a);
-        case 2: return launch_v2<8, 5, 2, 184, 4, 2>(h, a);
-        case 3: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);
-        case 4: return launch_v2<8, 4, 4, 224, 4, 2>(h, a);
-        case 5: return launch_v2<8, 3, 2, 255, 3, 2>(h, a);
-        case 6: return launch_v2<8, 3, 4, 224, 3, 4>(h, a);
-        case 7: return launch_v2<8, 2, 4, 255, 2, 4>(h, a);
-        case 8: return launch_v2<8, 2, 8, 255, 2, 4>(h, a);
-        case 9: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);
+        case 3: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);   // the DFMA (v2) kernel at lx = 8, for A/B runs
         case 20: return launch_v3<4, 4, 1, 128, 3, 1>(h, a); // 16 warps, 184 KB
         case 21: return launch_v3<3, 4, 2, 168, 3, 1>(h, a); // 12 warps, 222 KB
         case 22: return launch_v3<2, 8, 1, 128>(h, a);       // 16 warps, 1 plane per warp
@@ -709,9 +708,13 @@ void free_shared(Handle* h) {
 }
 
 void free_xstage(Handle* h) {
-  cudaFree(h->xs_link); cudaFree(h->xs_off); cudaFree(h->xs_dof); cudaFree(h->xs_skip);
-  h->xs_link = nullptr; h->xs_off = h->xs_dof = nullptr; h->xs_skip = nullptr;
-  h->xs_valid = false; h->xs_nclass = 0; h->xs_nslots = 0; h->xs_nlinked = 0; h->xs_nmember = 0;
+  for (int a = 0; a < 3; a++) {
+    cudaFree(h->xs_mask[a]); cudaFree(h->xs_pred[a]);
+    h->xs_mask[a] = nullptr; h->xs_pred[a] = nullptr; h->xs_have[a] = false;
+  }
+  cudaFree(h->xs_off); cudaFree(h->xs_dof); cudaFree(h->xs_skip);
+  h->xs_off = h->xs_dof = nullptr; h->xs_skip = nullptr;
+  h->xs_valid = false; h->xs_nclass = 0; h->xs_nslots = 0; h->xs_nlinked = 0; h->xs_nmember = 0; h->xs_level = 0;
 }
 
 // frees device temporaries on every exit path of a set-up routine
@@ -727,17 +730,23 @@ struct DevTemps {
   }
 };
 
-// x stage of the lx = 8 element kernel: link flags per element + CSR lists of the classes left to the
-// gather-scatter pass (gs_kernels.cuh "x stage").  Needs gs_init (and gs_init_shared, if any) done.
-int build_xstage(Handle* h) {
+// Staged direct-stiffness summation (gs_kernels.cuh "staged"): per-element face masks / neighbours and the CSR
+// lists of the classes left to the class-list pass.  Needs gs_init (and gs_init_shared, if any) done.
+int build_xstage(Handle* h, int level) {
   free_xstage(h);
   if (!h->have_gs || h->lx != 8 || h->nelv == 0) return B200_OK;
   cudaStream_t st = h->stream;
   const int nc = h->nclass, ne = h->nelv, threads = 256;
   const int nslots = std::min((ne + XS_NE - 1) / XS_NE, h->num_sm) * XS_NE;
-  if (int r = dmalloc(&h->xs_link, (size_t)ne)) return r;
-  CK(cudaMemsetAsync(h->xs_link, 0, (size_t)ne, st));
+  const int dirs = (level >= 2) ? 7 : 1;
+  for (int a = 0; a < 3; a++) {
+    if (int r = dmalloc(&h->xs_mask[a], (size_t)ne)) return r;
+    if (int r = dmalloc(&h->xs_pred[a], (size_t)ne)) return r;
+    CK(cudaMemsetAsync(h->xs_mask[a], 0, sizeof(unsigned long long) * (size_t)ne, st));
+    CK(cudaMemsetAsync(h->xs_pred[a], 0xff, sizeof(int) * (size_t)ne, st));
+  }
   h->xs_nslots = nslots;
+  h->xs_level = level;
   if (nc == 0) {
     if (int r = dmalloc(&h->xs_off, 1)) return r;
     if (int r = dmalloc(&h->xs_dof, 1)) return r;
@@ -746,21 +755,36 @@ int build_xstage(Handle* h) {
     return B200_OK;
   }
   DevTemps T;
-  int *d_cnt = nullptr, *d_keep = nullptr, *d_mem = nullptr, *d_newidx = nullptr, *d_newoff = nullptr;
-  if (int r = T.alloc(&d_cnt, (size_t)ne)) return r;
+  SgArrays A;
+  for (int a = 0; a < 3; a++) {
+    if (int r = T.alloc(&A.cnt[a], (size_t)ne)) return r;
+    if (int r = T.alloc(&A.pmin[a], (size_t)ne)) return r;
+    if (int r = T.alloc(&A.pmax[a], (size_t)ne)) return r;
+    if (int r = T.alloc(&A.succ[a], (size_t)ne)) return r;
+    if (int r = T.alloc(&A.scnt[a], (size_t)ne)) return r;
+    A.pred[a] = h->xs_pred[a];
+    A.mask[a] = h->xs_mask[a];
+    CK(cudaMemsetAsync(A.cnt[a], 0, sizeof(int) * (size_t)ne, st));
+    CK(cudaMemsetAsync(A.pmin[a], 0x7f, sizeof(int) * (size_t)ne, st));      // 0x7f7f7f7f: above every element index
+    CK(cudaMemsetAsync(A.pmax[a], 0xff, sizeof(int) * (size_t)ne, st));      // -1
+    CK(cudaMemsetAsync(A.succ[a], 0xff, sizeof(int) * (size_t)ne, st));
+    CK(cudaMemsetAsync(A.scnt[a], 0, sizeof(int) * (size_t)ne, st));
+  }
+  int *d_keep = nullptr, *d_mem = nullptr, *d_newidx = nullptr, *d_newoff = nullptr;
   if (int r = T.alloc(&d_keep, (size_t)nc)) return r;
   if (int r = T.alloc(&d_mem, (size_t)nc)) return r;
   if (int r = T.alloc(&d_newidx, (size_t)nc)) return r;
   if (int r = T.alloc(&d_newoff, (size_t)nc)) return r;
-  CK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (size_t)ne, st));
-  const int gc = grid_for(nc, threads, h->num_sm, 8);
+  const int gc = grid_for(nc, threads, h->num_sm, 8), ge = grid_for(ne, threads, h->num_sm, 8);
   if (!h->xs_nolink) {
-    xs_candidate_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, d_cnt);
+    sg_links_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, h->gs_skip, nc, ne, nslots, dirs, A);
+    LAUNCHED();
+    sg_elem_kernel<<<ge, threads, 0, st>>>(ne, A);
+    LAUNCHED();
+    sg_succ_kernel<<<ge, threads, 0, st>>>(ne, A);
     LAUNCHED();
   }
-  xs_link_kernel<<<grid_for(ne, threads, h->num_sm, 8), threads, 0, st>>>(d_cnt, ne, h->xs_link);
-  LAUNCHED();
-  xs_keep_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, nc, ne, nslots, h->xs_link, d_keep, d_mem);
+  sg_classify_kernel<<<gc, threads, 0, st>>>(h->gs_off, h->gs_dof, h->gs_skip, nc, dirs, A, d_keep, d_mem);
   LAUNCHED();
   CK(cudaGetLastError());
   void* d_tmp = nullptr;
@@ -775,7 +799,20 @@ int build_xstage(Handle* h) {
   CK(cudaMemcpyAsync(&last[1], d_keep + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&last[2], d_newoff + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&last[3], d_mem + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  // which directions have any staged node at all (an empty face pass is not launched)
+  unsigned long long* d_any = nullptr;
+  if (int r = T.alloc(&d_any, 3)) return r;
+  for (int a = 0; a < 3; a++) {
+    void* d_t2 = nullptr;
+    size_t tb = 0;
+    CK(cub::DeviceReduce::Max(nullptr, tb, h->xs_mask[a], d_any + a, ne, st));
+    if (int r = T.alloc(reinterpret_cast<unsigned char**>(&d_t2), tb)) return r;
+    CK(cub::DeviceReduce::Max(d_t2, tb, h->xs_mask[a], d_any + a, ne, st));
+  }
+  unsigned long long any[3] = {};
+  CK(cudaMemcpyAsync(any, d_any, sizeof any, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  for (int a = 0; a < 3; a++) h->xs_have[a] = any[a] != 0ull;
   const int nkeep = last[0] + last[1], nmem = last[2] + last[3];
   if (int r = dmalloc(&h->xs_off, (size_t)nkeep + 1)) return r;
   if (int r = dmalloc(&h->xs_dof, (size_t)nmem)) return r;
@@ -788,8 +825,25 @@ int build_xstage(Handle* h) {
   CK(cudaStreamSynchronize(st));
   h->xs_nclass = nkeep;
   h->xs_nmember = nmem;
-  h->xs_nlinked = ((int64_t)nc - nkeep) / 36;
+  h->xs_nlinked = (int64_t)nc - nkeep;       // classes staged
   h->xs_valid = true;
+  return B200_OK;
+}
+
+// y and z face passes of the staged summation (after the element kernel, y before z: both touch the i-edges)
+int gs_face_passes(Handle* h, double* f0, double* f1, double* f2) {
+  if (h->xs_level < 2) return B200_OK;
+  const int threads = 256;
+  const int grid = grid_for((int64_t)h->nelv * 32, threads, h->num_sm, 8);
+  if (h->xs_have[1]) {
+    gs_face_pass_kernel<1><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->xs_pred[1], h->xs_mask[1], h->nelv);
+    LAUNCHED();
+  }
+  if (h->xs_have[2]) {
+    gs_face_pass_kernel<2><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->xs_pred[2], h->xs_mask[2], h->nelv);
+    LAUNCHED();
+  }
+  CK(cudaGetLastError());
   return B200_OK;
 }
 
@@ -942,7 +996,7 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   g = getenv("B200_GS_L2HINT");
   if (g) h->gs_l2hint = atoi(g) != 0;
   g = getenv("B200_XSTAGE");
-  if (g) h->xs_enable = atoi(g) != 0;
+  if (g) h->xs_enable = std::min(2, std::max(0, atoi(g)));
   g = getenv("B200_XS_NOLINK");
   if (g) h->xs_nolink = atoi(g) != 0;
   *handle = h;
@@ -1095,8 +1149,8 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
   const bool masked_lube = a.sources && h->if_lube && h->lube_mask_size > 0;
   bool xs = h->xs_enable && uses_v3(h) && h->gs_mode == 0 && !h->d_order && !masked_lube &&
             !(mgpu && h->overlap_elem) && !(h->comm && h->nshared > 0 && !mgpu);
-  if (xs && !h->xs_valid) {
-    if (int r = build_xstage(h)) return r;
+  if (xs && (!h->xs_valid || h->xs_level != h->xs_enable)) {
+    if (int r = build_xstage(h, h->xs_enable)) return r;
     xs = h->xs_valid;
   }
   if (mgpu && !h->overlap_elem) {
@@ -1117,6 +1171,7 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     if (int r = phase_mark(h, 2)) return r;
     if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
     if (int r = phase_mark(h, 3)) return r;
+    if (xs) if (int r = gs_face_passes(h, f0, f1, f2)) return r;
     if (int r = gs_step_pass(h, f0, f1, f2, xs)) return r;
     if (int r = phase_mark(h, 4)) return r;
     if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
@@ -1192,6 +1247,7 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
       if (int r = gs_packed(h, f0, f1, f2)) return r;
       if (int r = gs_leftover(h, f0, f1, f2)) return r;
     } else if (a.xstage) {
+      if (int r = gs_face_passes(h, f0, f1, f2)) return r;
       if (int r = gs_step_pass(h, f0, f1, f2, true)) return r;
     } else {
       if (int r = gs_launch(h, f0, f1, f2, 3)) return r;
@@ -1247,17 +1303,17 @@ int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, in
 
 int b200_adjrhs_set_xstage(void* handle, const int* flag) {
   if (!handle || !flag) return fail(B200_ERR_ARG, "set_xstage: null argument");
-  H(handle)->xs_enable = (*flag != 0);
+  H(handle)->xs_enable = std::min(2, std::max(0, *flag));
   return B200_OK;
 }
 
-int b200_adjrhs_xstage_info(void* handle, int* active, int64_t* linked_elements, int64_t* classes_left,
+int b200_adjrhs_xstage_info(void* handle, int* active, int64_t* classes_staged, int64_t* classes_left,
                             int64_t* classes_total) {
   if (!handle) return fail(B200_ERR_ARG, "null handle");
   Handle* h = H(handle);
-  const bool on = h->xs_enable && h->xs_valid;
-  if (active) *active = on ? 1 : 0;
-  if (linked_elements) *linked_elements = on ? h->xs_nlinked : 0;
+  const bool on = h->xs_enable && h->xs_valid && h->xs_level == h->xs_enable;
+  if (active) *active = on ? h->xs_level : 0;
+  if (classes_staged) *classes_staged = on ? h->xs_nlinked : 0;
   if (classes_left) *classes_left = on ? h->xs_nclass : h->nclass;
   if (classes_total) *classes_total = h->nclass;
   return B200_OK;

@@ -369,54 +369,208 @@ __global__ void __launch_bounds__(256) gs_wide_kernel(double* __restrict__ f0, d
   }
 }
 
-// ---- x stage of the lx = 8 element kernel (adjrhs_kernel_v3.cuh, XS) -----------------------------------------
-// The element kernel sums, in registers, the 36 face-interior pair classes between element e-1 (i = 7) and
-// element e (i = 0) when the two faces are glued node by node with the same (j,k) orientation and both
-// elements are processed consecutively by one slot.  Set-up verifies this against the class lists:
-//   xs_candidate_kernel: a 2-member class {(e-1; 7,j,k), (e; 0,j,k)}, 1 <= j,k <= 6, e not the first element of a
-//                        slot's run, counts one for element e;
-//   xs_link_kernel:      xlink[e] = all 36 classes of the face were found;
-//   xs_keep_kernel:      a class stays in the gather-scatter pass unless it is such a pair of a linked element.
-// Runs: xs_run_begin / xs_is_run_start in adjrhs_kernel_v3.cuh (one contiguous run of elements per slot).
-// returns the later element of the pair if class c matches the pattern, else -1
-__device__ __forceinline__ int xs_pair_elem(const int* __restrict__ off, const int* __restrict__ dof, int c,
-                                            int nelem, int nslots) {
-  const int b = off[c];
-  if (off[c + 1] - b != 2) return -1;
-  const int d0 = dof[b], d1 = dof[b + 1];
-  const int e0 = d0 >> 9, e1 = d1 >> 9;
-  if (e1 != e0 + 1) return -1;
-  const int l0 = d0 & 511, l1 = d1 & 511;
-  if ((l0 & 7) != 7 || (l1 & 7) != 0 || (l0 >> 3) != (l1 >> 3)) return -1;
-  const int j = (l0 >> 3) & 7, k = l0 >> 6;
-  if (j < 1 || j > 6 || k < 1 || k > 6) return -1;
-  if (xs_is_run_start(e1, nelem, nslots)) return -1;
-  return e1;
+// ---- staged direct-stiffness summation for lx = 8 (adjrhs_kernel_v3.cuh XS + the face passes below) -----------
+// On a conforming hexahedral mesh most node classes are PRODUCTS of face pairings: a face-interior node is
+// shared by the two elements glued at that face, an edge node by 2x2 and a vertex by 2x2x2 elements.  For such
+// a class the sum over all members equals pair sums taken direction by direction -- x pairs, then y pairs of
+// the x sums, then z pairs -- and every copy ends with the same bits (a + b is commutative).  The step uses this:
+//   X  inside the element kernel: element e-1 (i = 7) and e (i = 0) when both are consecutive in one slot's run;
+//   Y  gs_face_pass_kernel<1>: element A (j = 7) and B (j = 0), rows of 64 contiguous bytes;
+//   Z  gs_face_pass_kernel<2>: element A (k = 7) and B (k = 0), planes of 512 contiguous bytes;
+// and only the classes that are NOT such products (irregular topology, partition-boundary classes, run starts)
+// stay in the class-list pass.  The face passes read and write whole sectors -- no index lists, no sector waste.
+// Set-up (all on the device, verified against the class lists of b200_gs_init, nothing assumed about the mesh):
+//   sg_links_kernel     face-interior 2-member classes vote for the face links of their elements;
+//   sg_elem_kernel      a link exists if all 36 interior classes of the face agree on ONE neighbour element;
+//   sg_succ_kernel      the inverse maps (a j = 7 / k = 7 face may be claimed by one element only);
+//   sg_classify_kernel  a class of 2, 4 or 8 members is staged iff every member has a partner in exactly the
+//                       same set A of directions, 2^|A| = size, the partner maps are involutions that commute and
+//                       stay inside the class; its nodes then get their bit in the per-element 64-bit masks
+//                       xmask (i = 0 face, bit j + 8k), ymask (j = 0 face, bit i + 8k), zmask (k = 0 face, bit i + 8j).
+// dirs: bit 0 = X, 1 = Y, 2 = Z allowed (dirs = 1: only the x pairs, results bit-identical to the plain pass).
+struct SgArrays {
+  int* cnt[3];              // votes per element and direction (the element owning the i/j/k = 0 face)
+  int* pmin[3];             // smallest / largest neighbour element voted for
+  int* pmax[3];
+  int* pred[3];             // neighbour across the i/j/k = 0 face (-1: no link); X: always e-1
+  int* succ[3];             // neighbour across the i/j/k = 7 face
+  int* scnt[3];
+  unsigned long long* mask[3];
+};
+__device__ __forceinline__ void sg_decode(int d, int& e, int (&x)[3]) {
+  e = d >> 9;
+  x[0] = d & 7; x[1] = (d >> 3) & 7; x[2] = (d >> 6) & 7;
 }
-__global__ void xs_candidate_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass,
-                                    int nelem, int nslots, int* __restrict__ cnt) {
+__device__ __forceinline__ int sg_encode(int e, const int (&x)[3]) { return (e << 9) | x[0] | (x[1] << 3) | (x[2] << 6); }
+
+__global__ void sg_links_kernel(const int* __restrict__ off, const int* __restrict__ dof,
+                                const unsigned char* __restrict__ skip, int nclass, int nelem, int nslots, int dirs,
+                                SgArrays A) {
   const int stride = gridDim.x * blockDim.x;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
-    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots);
-    if (e1 >= 0) atomicAdd(cnt + e1, 1);
+    const int b = off[c];
+    if (off[c + 1] - b != 2 || (skip && skip[c])) continue;
+    int e0, e1, x0[3], x1[3];
+    sg_decode(dof[b], e0, x0);
+    sg_decode(dof[b + 1], e1, x1);
+    if (e0 == e1) continue;
+    for (int a = 0; a < 3; a++) {
+      if (!(dirs >> a & 1)) continue;
+      const int u = (a + 1) % 3, v = (a + 2) % 3;
+      if (x0[u] != x1[u] || x0[v] != x1[v] || x0[u] < 1 || x0[u] > 6 || x0[v] < 1 || x0[v] > 6) continue;
+      int lo = -1, hi = -1;                         // hi owns the "0" face, lo the "7" face
+      if (x0[a] == 7 && x1[a] == 0) { lo = e0; hi = e1; }
+      else if (x0[a] == 0 && x1[a] == 7) { lo = e1; hi = e0; }
+      else continue;
+      if (a == 0 && (hi != lo + 1 || xs_is_run_start(hi, nelem, nslots))) continue;   // x: consecutive in one run
+      atomicAdd(A.cnt[a] + hi, 1);
+      atomicMin(A.pmin[a] + hi, lo);
+      atomicMax(A.pmax[a] + hi, lo);
+    }
   }
 }
-__global__ void xs_link_kernel(const int* __restrict__ cnt, int nelem, unsigned char* __restrict__ xlink) {
+__global__ void sg_elem_kernel(int nelem, SgArrays A) {
   const int stride = gridDim.x * blockDim.x;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride) xlink[e] = (cnt[e] == 36) ? 1 : 0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride)
+    for (int a = 0; a < 3; a++) {
+      const bool ok = A.cnt[a][e] == 36 && A.pmin[a][e] == A.pmax[a][e];
+      const int pr = ok ? A.pmin[a][e] : -1;
+      A.pred[a][e] = pr;
+      if (pr >= 0) { atomicAdd(A.scnt[a] + pr, 1); A.succ[a][pr] = e; }
+    }
 }
-// keep[c] = 1 / members[c] = class size if the class stays in the pass, else 0 / 0
-__global__ void xs_keep_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass, int nelem,
-                               int nslots, const unsigned char* __restrict__ xlink, int* __restrict__ keep,
-                               int* __restrict__ members) {
+__global__ void sg_succ_kernel(int nelem, SgArrays A) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride)
+    for (int a = 0; a < 3; a++) {
+      const int pr = A.pred[a][e];
+      if (pr >= 0 && A.scnt[a][pr] != 1) A.pred[a][e] = -1;
+      if (A.scnt[a][e] != 1) A.succ[a][e] = -1;
+    }
+}
+// partner of node (e, x) in direction a through the verified face links, or -1
+__device__ __forceinline__ int sg_partner(int e, const int (&x)[3], int a, const SgArrays& A) {
+  int y[3] = {x[0], x[1], x[2]};
+  int pe = -1;
+  if (x[a] == 0) { pe = A.pred[a][e]; y[a] = 7; }
+  else if (x[a] == 7) { pe = A.succ[a][e]; y[a] = 0; }
+  if (pe < 0) return -1;
+  return sg_encode(pe, y);
+}
+__global__ void sg_classify_kernel(const int* __restrict__ off, const int* __restrict__ dof,
+                                   const unsigned char* __restrict__ skip, int nclass, int dirs, SgArrays A,
+                                   int* __restrict__ keep, int* __restrict__ members) {
   const int stride = gridDim.x * blockDim.x;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nclass; c += stride) {
-    const int e1 = xs_pair_elem(off, dof, c, nelem, nslots);
-    const bool k = !(e1 >= 0 && xlink[e1]);
-    keep[c] = k ? 1 : 0;
-    members[c] = k ? off[c + 1] - off[c] : 0;
+    const int b = off[c], m = off[c + 1] - b;
+    bool staged = false;
+    int d[8], par[8][3];
+    int dirset = 0;
+    if ((m == 2 || m == 4 || m == 8) && !(skip && skip[c])) {
+      for (int i = 0; i < m; i++) d[i] = dof[b + i];
+      staged = true;
+      for (int i = 0; i < m && staged; i++) {
+        int e, x[3];
+        sg_decode(d[i], e, x);
+        int have = 0;
+        for (int a = 0; a < 3; a++) {
+          par[i][a] = -1;
+          if (!(dirs >> a & 1)) continue;
+          const int pd = sg_partner(e, x, a, A);
+          if (pd < 0) continue;
+          int idx = -1;
+          for (int t = 0; t < m; t++) if (d[t] == pd) idx = t;
+          if (idx < 0 || idx == i) { staged = false; break; }       // the link leaves the class: not a product
+          par[i][a] = idx;
+          have |= 1 << a;
+        }
+        if (i == 0) dirset = have;
+        else if (have != dirset) staged = false;
+      }
+      if (staged && (dirset == 0 || (1 << __popc(dirset)) != m)) staged = false;
+      for (int i = 0; i < m && staged; i++)
+        for (int a = 0; a < 3 && staged; a++) {
+          if (!(dirset >> a & 1)) continue;
+          const int pa = par[i][a];
+          if (par[pa][a] != i) staged = false;                                       // involution
+          for (int a2 = a + 1; a2 < 3 && staged; a2++)
+            if ((dirset >> a2 & 1) && par[pa][a2] != par[par[i][a2]][a]) staged = false;   // commute
+        }
+      if (staged) {
+        for (int i = 0; i < m; i++) {
+          int e, x[3];
+          sg_decode(d[i], e, x);
+          for (int a = 0; a < 3; a++) {
+            if (!(dirset >> a & 1) || x[a] != 0) continue;
+            const int u = (a + 1) % 3, v = (a + 2) % 3;
+            // bit layout: X (j + 8k), Y (i + 8k), Z (i + 8j): the lower of the two other indices first
+            const int lo = (a == 0) ? x[1] : x[0], hi = (a == 2) ? x[1] : x[2];
+            (void)u; (void)v;
+            atomicOr(A.mask[a] + e, 1ull << (lo + 8 * hi));
+          }
+        }
+      }
+    }
+    keep[c] = staged ? 0 : 1;
+    members[c] = staged ? 0 : m;
   }
 }
+
+// Y (DIR = 1) / Z (DIR = 2) face pass: one warp per element B with a non-empty mask; A = pred[B].  Lane l handles
+// the node pair (i = 2(l&3), +1) of row (l>>2): for Y the row index is k (rows j = 0 of B, j = 7 of A: 64
+// contiguous bytes each), for Z it is j (the planes k = 0 of B, k = 7 of A: 512 contiguous bytes).
+// 128-bit load that asks L2 to fetch no more than the 64 bytes it touches: a j-row is half of a 128-byte line, and
+// the default fetch granularity brings the other half (the row j = 1 or 6) from DRAM as well (ncu r02i: the y
+// pass read 1.59 GB for 0.80 GB of rows)
+__device__ __forceinline__ double2 ld_f64x2_l2_64(const double* p) {
+  double2 v;
+  asm volatile("ld.global.L2::64B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+template <int DIR>
+__global__ void __launch_bounds__(256) gs_face_pass_kernel(double* __restrict__ f0, double* __restrict__ f1,
+                                                          double* __restrict__ f2, const int* __restrict__ pred,
+                                                          const unsigned long long* __restrict__ mask, int nelem) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int r = lane >> 2, i = 2 * (lane & 3);
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nelem; e += warps) {
+    const unsigned long long m = mask[e];
+    if (m == 0ull) continue;
+    const int pe = pred[e];
+    const unsigned bits = (unsigned)(m >> (i + 8 * r)) & 3u;
+    if (bits == 0u) continue;
+    const size_t ob = (size_t)e * 512 + (DIR == 1 ? 64 * r : 8 * r) + i;                    // (i, 0, r) or (i, r, 0)
+    const size_t oa = (size_t)pe * 512 + (DIR == 1 ? 64 * r + 56 : 8 * r + 448) + i;        // (i, 7, r) or (i, r, 7)
+    double* fs[3] = {f0, f1, f2};
+    double2 va[3], vb[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (DIR == 1) {
+        va[c] = ld_f64x2_l2_64(fs[c] + oa);
+        vb[c] = ld_f64x2_l2_64(fs[c] + ob);
+      } else {
+        va[c] = *reinterpret_cast<const double2*>(fs[c] + oa);
+        vb[c] = *reinterpret_cast<const double2*>(fs[c] + ob);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double2 s;
+      s.x = va[c].x + vb[c].x;
+      s.y = va[c].y + vb[c].y;
+      if (bits == 3u) {
+        *reinterpret_cast<double2*>(fs[c] + oa) = s;
+        *reinterpret_cast<double2*>(fs[c] + ob) = s;
+      } else if (bits == 1u) {
+        fs[c][oa] = s.x; fs[c][ob] = s.x;
+      } else {
+        fs[c][oa + 1] = s.y; fs[c][ob + 1] = s.y;
+      }
+    }
+  }
+}
+
 // compacted CSR of the kept classes (+ their shared-node skip flags)
 __global__ void xs_compact_kernel(const int* __restrict__ off, const int* __restrict__ dof, int nclass,
                                   const int* __restrict__ keep, const int* __restrict__ newidx,

@@ -305,12 +305,12 @@ module neko_top_b200
      end function b200_adjrhs_set_xstage
 
      integer(c_int) function b200_adjrhs_xstage_info(handle, active, &
-          linked_elements, classes_left, classes_total) &
+          classes_staged, classes_left, classes_total) &
           bind(c, name='b200_adjrhs_xstage_info')
        use, intrinsic :: iso_c_binding
        type(c_ptr), value :: handle
        integer(c_int) :: active
-       integer(c_int64_t) :: linked_elements, classes_left, classes_total
+       integer(c_int64_t) :: classes_staged, classes_left, classes_total
      end function b200_adjrhs_xstage_info
 
      integer(c_int) function b200_adjrhs_set_dealias(handle, flag) &

@@ -541,15 +541,16 @@ class fused_adjoint_rhs_t:
         check(_lib.lib().b200_adjrhs_gs_info(self._hd.h, C.byref(a), C.byref(b), C.byref(c)))
         return bool(a.value), b.value, c.value
 
-    def set_xstage(self, flag=True):
-        """i-face pair classes of consecutive elements summed inside the lx = 8 element kernel (default on)."""
-        check(_lib.lib().b200_adjrhs_set_xstage(self._hd.h, _ci(flag)))
+    def set_xstage(self, level=2):
+        """Staged direct-stiffness summation at lx = 8: 0 off, 1 = x pairs in the element kernel (bit-identical),
+        2 = product classes summed direction by direction (x in the kernel, y / z face passes; default)."""
+        check(_lib.lib().b200_adjrhs_set_xstage(self._hd.h, _ci(int(level))))
 
     def xstage_info(self):
-        """(active, elements linked to their predecessor, classes left to the gs pass, classes in total)."""
+        """(level in use, classes staged, classes left to the class-list pass, classes in total)."""
         a, b, c, d = C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
         check(_lib.lib().b200_adjrhs_xstage_info(self._hd.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return bool(a.value), b.value, c.value, d.value
+        return a.value, b.value, c.value, d.value
 
     def enable_timing(self, flag=True):
         check(_lib.lib().b200_adjrhs_enable_timing(self._hd.h, _ci(flag)))

@@ -57,15 +57,17 @@ def main():
     n = brick.n
     mk = lambda: [torch.full((n,), float("nan"), device=dev, dtype=torch.float64) for _ in range(3)]
     results = {}
-    for mode in ("sequential", "no_xstage", "overlap", "overlap_gs1", "overlap_gs2"):
+    for mode in ("staged", "sequential", "no_xstage", "overlap", "overlap_gs1", "overlap_gs2"):
         # sequential = the default path (exchange overlapped with the local gs); with
         # B200_EXCHANGE_OVERLAP=elem the "overlap*" modes run the boundary/interior split
-        if mode == "sequential":
-            op.set_xstage(True)
+        if mode == "staged":                   # the default: product classes summed direction by direction
+            op.set_xstage(2)
+        if mode == "sequential":               # x pairs in the kernel only: bit-identical to every mode below
+            op.set_xstage(1)
         if mode == "no_xstage":                # plain element kernel + full local pass
-            op.set_xstage(False)
+            op.set_xstage(0)
         if mode == "overlap":
-            op.set_xstage(True)
+            op.set_xstage(1)
             op.set_boundary_elements(sh.bnd_elem)
         if mode.startswith("overlap_gs"):      # packed class lists / summation inside the interior kernel
             op.set_gs_mode(int(mode[-1]))
@@ -73,7 +75,7 @@ def main():
         for _ in range(2):
             op.step(d["v"], d["ub"], f, rho=d["rho"], sens=sens)
         torch.cuda.synchronize()
-        if mode == "sequential":
+        if mode == "staged":
             xs_info = op.xstage_info()
         results[mode] = [a.cpu().numpy() for a in f] + [sens.cpu().numpy()]
     # host-buffer path
@@ -110,6 +112,9 @@ def main():
     op.set_gs_mode(0)
     same = all(np.array_equal(a, b) for m in ("no_xstage", "overlap", "overlap_gs1", "overlap_gs2")
                for a, b in zip(results["sequential"], results[m]))
+    # the staged sums associate 4- and 8-member classes pairwise: equal to the class-list sums up to rounding
+    same = same and all(np.abs(a - b).max() <= 4e-15 * np.abs(b).max()
+                        for a, b in zip(results["staged"], results["sequential"]))
     same_h = all(np.array_equal(a, b) for a, b in zip(results["sequential"], results["host"]))
     t = torch.tensor([worst, 0.0 if (same and same_h) else 1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -117,7 +122,7 @@ def main():
     if rank == 0:
         ok = t[0].item() <= 1e-12 and t[1].item() == 0.0
         print(f"MGPU_CHECK world={world} ne={ne} lx={lx} nshared(rank0)={sh.nshared} nbnd(rank0)={sh.bnd_elem.size} "
-              f"xstage(rank0: active, linked elements, classes left, total)={xs_info} "
+              f"xstage(rank0: level, classes staged, classes left, total)={xs_info} "
               f"max_err={t[0].item():.3e} modes_bit_identical={t[1].item() == 0.0} -> {'PASS' if ok else 'FAIL'}",
               flush=True)
     op.free()

@@ -447,7 +447,8 @@ class gs_t:
             if candidates is not None:
                 c = candidates.contiguous().view(-1).to(torch.uint8)
                 assert c.is_cuda and c.numel() == self._hd.n
-            check(_lib.lib().b200_gs_init_shared_from_keys(self._hd.h, _ptr(k), _ci(1), _ptr(c), C.byref(ns), C.byref(nn)))
+            cp = None if c is None else C.c_void_p(c.data_ptr())
+            check(_lib.lib().b200_gs_init_shared_from_keys(self._hd.h, _ptr(k), _ci(1), cp, C.byref(ns), C.byref(nn)))
             torch.cuda.synchronize()
         else:
             k = np.ascontiguousarray(np.asarray(keys).reshape(-1), dtype=np.int64)

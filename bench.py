@@ -391,7 +391,26 @@ def run_b200(args):
                "matches_device_path": bool(e2e_ok), "max_rel_diff_vs_device_path": e2e_diff,
                "note": "b200_adjrhs_step_host: 7 input fields H2D from pinned memory, f(3)+sens D2H, "
                        "geometry resident (set once like coef_t); bytes are per rank"}
-        del hv, hub, hrho, hf, hs
+        # what bounds e2e: the host link of this rank while ALL ranks copy at the same time (one VM, shared PCIe
+        # switches / host memory): 1 GiB pinned H2D and D2H, concurrently in both directions like the pipelined step
+        nb = min(n, 1 << 27)
+        dbuf = torch.empty(nb, device=dev, dtype=torch.float64)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            dbuf.copy_(hv[0][:nb], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hf[0][:nb].copy_(f[0][:nb], non_blocking=True)
+        torch.cuda.synchronize()
+        dt_link = maxr(time.perf_counter() - t0)
+        link = nb * 8 / dt_link / 1e9
+        e2e["host_link"] = {"GBps_each_direction_per_rank": link, "ranks_concurrent": N,
+                            "floor_ms_per_step": 7 * n * 8 / (link * 1e9) * 1e3,
+                            "note": "1 GiB pinned H2D + 1 GiB D2H at once on every rank; floor = the 7 input fields "
+                                    "at that rate (outputs overlap in the other direction)"}
+        barrier()
+        del hv, hub, hrho, hf, hs, dbuf
 
     # ---- roofline of the dominant kernel (rank 0) ------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -554,11 +554,11 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     }
     named_bar_sync(bar_id, C::NSLOT_THR);
 
-    // ---- x stage: fetch the previous element's i = 7 values now (L2 hits, ~1 us under load), use them in the
-    //      final store phase: the latency hides behind the transposed t contraction and its barrier
     [[maybe_unused]] double pv[NPL][3];
     [[maybe_unused]] bool xdo[NPL];
-    if constexpr (XS == 2) {
+    // x stage: fetch the previous element's i = 7 values (L2 hits, ~1 us under load) before the transposed t
+    // contraction, whose work hides the latency (fetching right before the stores: +7 % step time, r02l)
+    auto xs_fetch = [&]() {
 #pragma unroll
       for (int pi = 0; pi < NPL; pi++) {
         const int k = wid + pi * NW;
@@ -569,7 +569,8 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
           for (int c = 0; c < 3; c++) pv[pi][c] = __ldcg(p.f[c] + xoff);
         }
       }
-    }
+    };
+    if constexpr (XS == 2) xs_fetch();
 
     // ---- transposed t contraction per (component, j) slab, in place in Wt ------------------------------
 #pragma unroll

@@ -396,19 +396,22 @@ def run_b200(args):
         nb = min(n, 1 << 27)
         dbuf = torch.empty(nb, device=dev, dtype=torch.float64)
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-        barrier()
-        t0 = time.perf_counter()
-        with torch.cuda.stream(s_in):
-            dbuf.copy_(hv[0][:nb], non_blocking=True)
-        with torch.cuda.stream(s_out):
-            hf[0][:nb].copy_(f[0][:nb], non_blocking=True)
-        torch.cuda.synchronize()
-        dt_link = maxr(time.perf_counter() - t0)
-        link = nb * 8 / dt_link / 1e9
+        link = 0.0
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_in):
+                dbuf.copy_(hv[0][:nb], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hf[0][:nb].copy_(f[0][:nb], non_blocking=True)
+            torch.cuda.synchronize()
+            dt_link = maxr(time.perf_counter() - t0)
+            link = max(link, nb * 8 / dt_link / 1e9)
         e2e["host_link"] = {"GBps_each_direction_per_rank": link, "ranks_concurrent": N,
-                            "floor_ms_per_step": 7 * n * 8 / (link * 1e9) * 1e3,
-                            "note": "1 GiB pinned H2D + 1 GiB D2H at once on every rank; floor = the 7 input fields "
-                                    "at that rate (outputs overlap in the other direction)"}
+                            "h2d_GBps_per_rank_in_step": 7 * n * 8 / (dt / args.e2e_steps) / 1e9,
+                            "note": "best of 3: 1 GiB pinned H2D + 1 GiB D2H at once on EVERY rank (slowest rank counts): "
+                                    "what the VM's host memory / PCIe switches give N concurrent ranks; the step moves "
+                                    "7 fields in and 4 out per rank at the rate shown"}
         barrier()
         del hv, hub, hrho, hf, hs, dbuf
 

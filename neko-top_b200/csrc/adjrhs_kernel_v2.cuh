@@ -90,13 +90,13 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* src, uint32_t bytes
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-template <int LX, int NE, int NS, int NF>
+template <int LX, int NE, int NS, int NF, int NPROD = 1>
 struct V2Cfg {
   static constexpr int N = LX * LX * LX;
   static constexpr int NCONS = LX * LX;
   static constexpr int NCWARP = (NCONS + 31) / 32;
   static constexpr int NCTHR = NCWARP * 32;
-  static constexpr int NTHREADS = NE * NCTHR + 32;
+  static constexpr int NTHREADS = NE * NCTHR + 32 * NPROD;      // NPROD producer warps, slots dealt round-robin
   static constexpr int PLANE = LX * LX;                    // doubles
   static constexpr int PLANE_BYTES = PLANE * 8;
   // Odd LX: a k-plane of a user field (LX*LX*8 bytes, = 8 mod 16) starts on a 16-byte boundary only for every
@@ -132,10 +132,10 @@ __device__ __forceinline__ void ldg_row(double (&u)[LX], const double* __restric
   }
 }
 
-template <int LX, int NE, int NS, int NF, int MAXREG>
-__global__ void __launch_bounds__(V2Cfg<LX, NE, NS, NF>::NTHREADS, 1) __maxnreg__(MAXREG)
+template <int LX, int NE, int NS, int NF, int MAXREG, int NPROD = 1>
+__global__ void __launch_bounds__(V2Cfg<LX, NE, NS, NF, NPROD>::NTHREADS, 1) __maxnreg__(MAXREG)
 adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
-  using C = V2Cfg<LX, NE, NS, NF>;
+  using C = V2Cfg<LX, NE, NS, NF, NPROD>;
   constexpr int N = C::N;
   constexpr int NCONS = C::NCONS;
   constexpr int NCTHR = C::NCTHR;
@@ -160,13 +160,16 @@ adjrhs_v2_kernel(const __grid_constant__ KParams2<LX> p) {
     // The whole warp runs this loop with warp-uniform control flow; one elected lane issues the copies.
     // (A `lane == 0` branch instead makes the compiler wrap every UBLKCP in a lane-serialisation loop,
     // ~20 instructions per copy, and the single producer becomes the bottleneck of the SM.)
-    const int lane = tid - NE * NCTHR;
+    // (NPROD > 1: producer warp w serves the slots s with s % NPROD == w -- one elected lane issues ~5 bulk copies
+    // per plane and slot, and at small lx a single warp cannot keep NE slots fed)
+    const int pw = (tid - NE * NCTHR) >> 5;
     int it[NE], kk[NE], st[NE], ph[NE], nmy[NE];
     int remaining = 0;
 #pragma unroll
     for (int s = 0; s < NE; s++) {
       const int g = (int)blockIdx.x * NE + s;
       nmy[s] = (p.nelem > g) ? (p.nelem - 1 - g) / nslots + 1 : 0;
+      if (NPROD > 1 && (s % NPROD) != pw) nmy[s] = 0;
       it[s] = 0; kk[s] = 0; st[s] = 0; ph[s] = 0;
       remaining += (nmy[s] > 0);
     }

@@ -130,6 +130,7 @@ struct Handle {
   int gs_mode = 0;                 // 0: CSR kernels (default, fastest), 1: packed class lists, 2: inside the v3 element kernel
   int gs_lag = 2;                  // B200_GS_LAG
   bool overlap_elem = false;       // B200_EXCHANGE_OVERLAP=elem: overlap the exchange with the interior-element kernel
+  bool exchange_side = false;      // B200_EXCHANGE_SIDE=1: shared-class sum + pack on the communication stream (r02n: no gain)
   int gs_un = 1;                   // classes in flight per thread in gs_op_kernel (B200_GS_UN: 1, 2, 4; measured: 1 is best)
   bool gs_l2hint = true;           // B200_GS_L2HINT=0: no evict_first policy on the streaming inputs
   bool sched_valid = false;
@@ -210,9 +211,9 @@ struct LaunchArgs {
 };
 
 // ---- second-generation kernel (adjrhs_kernel_v2.cuh): NE element slots + one TMA warp per SM ----------
-template <int LX, int NE, int NS, int NF, int MAXREG>
+template <int LX, int NE, int NS, int NF, int MAXREG, int NPROD = 1>
 int launch_v2_cfg(Handle* h, const LaunchArgs& a) {
-  using C = V2Cfg<LX, NE, NS, NF>;
+  using C = V2Cfg<LX, NE, NS, NF, NPROD>;
   static_assert(C::SMEM <= 227 * 1024, "v2 configuration exceeds the shared memory of an SM");
   static_assert(C::NTHREADS <= 1024, "v2 configuration exceeds 1024 threads");
   KParams2<LX> p;
@@ -259,7 +260,7 @@ int launch_v2_cfg(Handle* h, const LaunchArgs& a) {
   p.f_min = h->f_min; p.f_max = h->f_max; p.q = h->q; p.K_lube = h->K_lube;
   p.K_sens = h->if_lube ? h->K_sens : 0.0;
 
-  auto kern = adjrhs_v2_kernel<LX, NE, NS, NF, MAXREG>;
+  auto kern = adjrhs_v2_kernel<LX, NE, NS, NF, MAXREG, NPROD>;
   static unsigned long long attr_set = 0;   // per instantiation, one bit per device (the attribute is per device)
   if (h->device >= 64 || !(attr_set >> h->device & 1ull)) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -273,10 +274,10 @@ int launch_v2_cfg(Handle* h, const LaunchArgs& a) {
   return B200_OK;
 }
 
-template <int LX, int NE, int NS, int MAXREG, int NE_FULL = NE, int NS_FULL = NS>
+template <int LX, int NE, int NS, int MAXREG, int NE_FULL = NE, int NS_FULL = NS, int NPROD = 1>
 int launch_v2(Handle* h, const LaunchArgs& a) {
-  if (a.fs[0] || a.fin[0]) return launch_v2_cfg<LX, NE_FULL, NS_FULL, NF_FULL, MAXREG>(h, a);
-  return launch_v2_cfg<LX, NE, NS, NF_FUSED, MAXREG>(h, a);
+  if (a.fs[0] || a.fin[0]) return launch_v2_cfg<LX, NE_FULL, NS_FULL, NF_FULL, MAXREG, NPROD>(h, a);
+  return launch_v2_cfg<LX, NE, NS, NF_FUSED, MAXREG, NPROD>(h, a);
 }
 
 // ---- third-generation kernel (adjrhs_kernel_v3.cuh): lx = 8, DMMA contractions --------------------------
@@ -469,8 +470,12 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
     // split over four schedulers: 9-12 warps -> 168 registers, <= 8 warps -> 255); cfg 32 = the older choice.
     // (deeper plane rings -- 3..7 stages -- were measured in r02j: no gain at lx = 5, 6, 9, 10, +6 % at lx = 7 with 7
     // stages; the consumers' waits on the ring are the single producer lane's issue rate, not the ring depth)
-    case 5: return cfg == 32 ? launch_v2<5, 8, 2, 224>(h, a) : launch_v2<5, 11, 2, 168>(h, a);
-    case 6: return cfg == 32 ? launch_v2<6, 4, 2, 224>(h, a) : launch_v2<6, 5, 2, 168>(h, a);
+    // lx = 5, 6: several producer warps (ncu r02h / sweeps r02n, r02o): one elected lane issuing ~5 bulk copies per
+    // plane and slot could not keep the slots fed -- the consumers spun on the ring's mbarriers.  lx = 5: 8 slots
+    // + 4 producer warps 10.3 -> 16.9 GDOF/s; lx = 6: 4 slots + 4 producer warps 12.0 -> 14.8 GDOF/s.
+    // (2, 3, 5, 6 producer warps and other slot counts: r02n-r02p, all slower; cfg 32 = the round-1 single-producer choice)
+    case 5: return cfg == 32 ? launch_v2<5, 11, 2, 168>(h, a) : launch_v2<5, 8, 3, 168, 8, 2, 4>(h, a);
+    case 6: return cfg == 32 ? launch_v2<6, 5, 2, 168>(h, a) : launch_v2<6, 4, 3, 168, 4, 2, 4>(h, a);
     case 7: return cfg == 32 ? launch_v2<7, 4, 2, 224>(h, a) : launch_v2<7, 3, 7, 255, 3, 6>(h, a);
     case 8:
       switch (cfg) {
@@ -482,6 +487,7 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
         case 25: return launch_v3<3, 4, 1, 168>(h, a);       // 12 warps, 138 KB
         default: return launch_v3_default(h, a);
       }
+    // (two producer warps at lx = 7, 9, 10: -3 % / 0 / +3 %, r02n: these orders are bound by the consumers)
     case 9: return cfg == 32 ? launch_v2<9, 3, 2, 200>(h, a) : launch_v2<9, 2, 4, 255, 2, 2>(h, a);
     case 10: return launch_v2<10, 2, 2, 224>(h, a);
     default: return fail(B200_ERR_ARG, "lx=%d not instantiated (4..10)", h->lx);
@@ -561,16 +567,32 @@ int gs_step_pass(Handle* h, double* f0, double* f1, double* f2, bool xs) {
 }
 
 // shared-node exchange: pack -> ncclSend/Recv (comm stream) -> unpack
-int gs_exchange(Handle* h, double* f0, double* f1, double* f2, int nf) {
+// shared_first: first sum the classes that hold shared nodes; side_stream: run that sum and the pack on the
+// communication stream too (behind an event on the main stream), so that the main stream goes straight on to
+// the rank-local passes -- they touch disjoint nodes
+int gs_exchange(Handle* h, double* f0, double* f1, double* f2, int nf, bool shared_first = false,
+                bool side_stream = false) {
   if (!h->comm || h->nshared == 0) return B200_OK;
   const int threads = 256;
+  cudaStream_t ps = side_stream ? h->comm_stream : h->stream;
+  if (side_stream) {
+    CK(cudaEventRecord(h->ev_pack, h->stream));
+    CK(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+  }
+  if (shared_first && h->n_shared_cls > 0) {
+    const int gl = grid_for(h->n_shared_cls, threads, h->num_sm, 4);
+    gs_op_list_kernel<3><<<gl, threads, 0, ps>>>(f0, f1, f2, h->gs_off, h->gs_dof, h->gs_shared_cls, h->n_shared_cls);
+    LAUNCHED();
+  }
   const int grid = grid_for(h->nsend, threads, h->num_sm, 4);
-  if (nf == 1) gs_pack_kernel<1><<<grid, threads, 0, h->stream>>>(f0, f0, f0, h->d_send_dof, h->nsend, h->d_send);
-  else gs_pack_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->d_send_dof, h->nsend, h->d_send);
+  if (nf == 1) gs_pack_kernel<1><<<grid, threads, 0, ps>>>(f0, f0, f0, h->d_send_dof, h->nsend, h->d_send);
+  else gs_pack_kernel<3><<<grid, threads, 0, ps>>>(f0, f1, f2, h->d_send_dof, h->nsend, h->d_send);
   LAUNCHED();
   CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev_pack, h->stream));
-  CK(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+  if (!side_stream) {
+    CK(cudaEventRecord(h->ev_pack, h->stream));
+    CK(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+  }
   NK(ncclGroupStart());
   for (int j = 0; j < h->nneigh; j++) {
     const size_t o = (size_t)h->neigh_off[j] * nf, cnt = (size_t)(h->neigh_off[j + 1] - h->neigh_off[j]) * nf;
@@ -987,6 +1009,8 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   if (g) h->gs_mode = std::min(2, std::max(0, atoi(g)));
   g = getenv("B200_EXCHANGE_OVERLAP");
   if (g) h->overlap_elem = (strcmp(g, "elem") == 0);
+  g = getenv("B200_EXCHANGE_SIDE");
+  if (g) h->exchange_side = atoi(g) != 0;
   g = getenv("B200_PHASE_TIMING");
   if (g) h->phase_timing = atoi(g) != 0;
   g = getenv("B200_GS_UN");
@@ -1161,15 +1185,11 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     if (int r = masked_lube_post(h, a)) return r;
     if (int r = phase_mark(h, 1)) return r;
     if (int r = time_mark(h)) return r;
-    if (h->n_shared_cls > 0) {
-      const int threads = 256, grid = grid_for(h->n_shared_cls, threads, h->num_sm, 4);
-      gs_op_list_kernel<3><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->gs_off, h->gs_dof,
-                                                             h->gs_shared_cls, h->n_shared_cls);
-      LAUNCHED();
-      CK(cudaGetLastError());
-    }
+    // shared-class sum and pack, then the NCCL exchange on the communication stream while the main stream runs the
+    // rank-local passes (B200_EXCHANGE_SIDE=1 moves sum and pack to the communication stream too: measured
+    // 4.657 vs 4.629 ms at N = 2, r02n -- no gain)
     if (int r = phase_mark(h, 2)) return r;
-    if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
+    if (int r = gs_exchange(h, f0, f1, f2, 3, true, h->exchange_side)) return r;
     if (int r = phase_mark(h, 3)) return r;
     if (xs) if (int r = gs_face_passes(h, f0, f1, f2)) return r;
     if (int r = gs_step_pass(h, f0, f1, f2, xs)) return r;

@@ -49,3 +49,22 @@ for lx in (5, 6, 8):
     torch.cuda.synchronize()
     print("lx", lx, "ok", float(f[0].abs().sum()), flt.ksp_results[0])
     op.free()
+
+# staged direct-stiffness summation at lx = 8 (levels 0/1/2): more elements than element slots so that the slots
+# have runs with linked x faces, plus the y / z face passes and the set-up kernels; steady_simcomp update
+P = Problem(8, ne=(8, 8, 8), deform=0.02)
+coef = ops.coef_t(ops.space_t(P.lx, P.D, P.w), P.nelv, P.cuda("G"), P.cuda("B"))
+op = ops.fused_adjoint_rhs_t(coef)
+op.gs.init(P.keys.reshape(-1).cuda())
+v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+f = [torch.zeros(P.n, device="cuda", dtype=torch.float64) for _ in range(3)]
+for level in (0, 1, 2):
+    op.set_xstage(level)
+    op.step(v, ub, f, rho=rho)
+    torch.cuda.synchronize()
+    print("staged level", level, op.xstage_info(), float(f[0].abs().sum()))
+sc = ops.steady_simcomp_t()
+sc.init_from_attributes(1e-12, f)
+sc.compute_()
+print("steady", sc.normed_diff)
+op.free()

@@ -279,19 +279,18 @@ int b200_gs_init_shared_from_keys(void* handle, const int64_t* key, const int* o
 int b200_adjrhs_set_boundary_elements(void* handle, const int* nbnd, const int* bnd_elem);
 
 /* Processing order of the elements in the fused step (a permutation of 0..nelv-1, HOST; *nelem = 0
- * restores 0..nelv-1).  Results do not depend on it.  It only matters for the opt-in in-kernel summation
- * (b200_adjrhs_set_gs_fused), which pays only while the earlier members of a node class are still in L2 --
- * neighbouring elements should then be close in this order (workloads.tile_order); with the default separate
- * gather-scatter pass the mesh order is best (the element-list variant of the kernel is ~10 % slower). */
+ * restores 0..nelv-1).  Results do not depend on it.  The staged summation and the contiguous-run element
+ * kernel need the mesh order, so any order set here switches them off (and the element-list variant of the
+ * kernel is ~10 % slower): a diagnostic / experimentation hook. */
 int b200_adjrhs_set_element_order(void* handle, const int* nelem, const int* order);
-/* How b200_adjrhs_step sums the node classes (all three give bit-identical results):
- *   *flag = 0 (default)  separate pass over the CSR class lists (fastest measured);
- *   *flag > 0            inside the lx = 8 element kernel while f is still in L2 (experimental: removes the
- *                        pass's DRAM traffic but is L1-bound and slower; environment B200_GS_FUSED=1);
- *   *flag < 0            separate pass over the class lists packed by size (environment B200_GS_MODE=1). */
+/* Class-list pass of b200_adjrhs_step when the staged summation (b200_adjrhs_set_xstage) is not in use:
+ *   *flag = 0 (default)  CSR class lists;
+ *   *flag != 0           class lists packed by size, sorted by the element that completes them (the lists the
+ *                        pipelined b200_adjrhs_step_host walks; environment B200_GS_MODE=1).  Same bits either way.
+ * (Round 1's experimental summation inside the element kernel through completion counters is gone: the staged
+ * summation removes the same DRAM traffic without spin-waits.) */
 int b200_adjrhs_set_gs_fused(void* handle, const int* flag);
-/* *fused = 1 if b200_adjrhs_step currently sums node classes inside the element kernel;
- * *classes_in_kernel of *classes_total are handled there (the rest: shared-node path, > 16 members). */
+/* *fused = 0 (kept for ABI stability); *classes_in_kernel = classes in the packed lists when they are in use */
 int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, int64_t* classes_total);
 /* Staged direct-stiffness summation of b200_adjrhs_step at lx = 8 (environment B200_XSTAGE):
  *   *flag = 0  plain element kernel + gather-scatter pass over all class lists;

@@ -29,9 +29,7 @@ enum : unsigned {
   FLAG_SENS = 32u,
   FLAG_CHI_OUT = 64u,
   FLAG_CONVEX_UP = 128u,
-  FLAG_LINEAR = 256u,    // (reserved)
-  FLAG_GS = 512u,        // v3 kernel: direct-stiffness summation inside the element kernel
-  FLAG_L2HINT = 1024u    // v3 kernel: L2 evict_first policy on the streaming inputs / sens / chi
+  FLAG_LINEAR = 256u     // (reserved)
 };
 
 // ---- PTX helpers --------------------------------------------------------------------------------

@@ -54,14 +54,6 @@ struct KParams2 {
   int n_active;               // NGEO + number of non-NULL pf entries (expect_tx bytes)
   unsigned flags;
   double f_min, f_max, q, K_lube, K_sens;
-  // in-kernel gather-scatter schedule (adjrhs_kernel_v3.cuh, FLAG_GS); see gs_kernels.cuh "schedule"
-  const int4* gs_eoff;        // [nelem + 1]: first entry of position p in the pair/quad/oct/hex lists
-  const int2* gs_pair;        // node classes with 2 members
-  const int4* gs_quad;        // 3..4 members (-1 padded)
-  const int4* gs_oct;         // 5..8 members, 2 x int4 per class
-  const int4* gs_hex;         // 9..16 members, 4 x int4 per class
-  unsigned long long* gs_done;  // one counter per window of nslots consecutive positions (zeroed per launch)
-  int gs_lag;                 // windows between storing an element and summing its classes (>= 1)
   int elem_base;              // v2: added to every element index (field pointers stay 16-byte aligned for odd LX)
   const unsigned long long* xmask;  // v3 XS: bit (j + 8k) of xmask[e]: nodes (e-1; 7,j,k) and (e; 0,j,k) are summed in the kernel
 };

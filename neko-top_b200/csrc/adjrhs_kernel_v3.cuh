@@ -93,124 +93,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ---- direct-stiffness summation inside the element kernel (FLAG_GS) ---------------------------------------
-// The separate gs pass re-reads and re-writes all of f from HBM (every 32-byte sector holds a surface node):
-// 48 B/DOF on top of the element kernel's 168.  Here the summation runs while f is still in L2.
-//   * Elements are processed in list order; "position" p = index in that list.  The grid works on windows of
-//     nslots consecutive positions (one per element slot), so a node class is COMPLETE once every element up
-//     to the largest position among its members has been stored.
-//   * Set-up (capi.cu build_gs_schedule) sorts the classes by that completing position and packs them by
-//     member count into pair / quad / oct / hex lists; gs_eoff[p] = first entry of position p in each list.
-//   * After storing its element of window w a slot publishes it: bar.sync (slot) -> thread 0:
-//     red.release.gpu.add(gs_done[w]).  Every GSB iterations it sums the classes that completed at ITS positions
-//     of the windows up to LAG before the newest: each warp polls the window counters (acquire, L2) until the whole
-//     window is stored, then gathers with ld.global.cg (L2, never a stale L1 line), adds the members in
-//     ascending dof order (the oracle's order: results are bit-identical to gs_op_kernel) and scatters.
-//     All CTAs are co-resident (grid <= #SMs, 1 CTA/SM) and every slot publishes window w before it waits
-//     for window w, so the wait cannot deadlock.
-//   * The streaming inputs are loaded with an L2 evict_first policy so that they do not push f out of L2
-//     before its classes complete (a z-neighbour in a 16x16-element tile column is 256 positions away).
-// acquire at gpu scope: pairs with the publishers' red.release.gpu, so the gathers that follow the spin are
-// ordered after the stores of every slot counted in the value read
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// publish: release-add at gpu scope (orders the slot's earlier stores, made visible to this thread by the
-// slot barrier, before the counter update)
-__device__ __forceinline__ void red_release_add(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-template <int NT>
-__device__ __forceinline__ void gs_sum_members(double* __restrict__ f0, double* __restrict__ f1,
-                                               double* __restrict__ f2, const int (&d)[NT]) {
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-  for (int m = 0; m < NT; m++)
-    if (d[m] >= 0) { s0 += __ldcg(f0 + d[m]); s1 += __ldcg(f1 + d[m]); s2 += __ldcg(f2 + d[m]); }
-#pragma unroll
-  for (int m = 0; m < NT; m++)
-    if (d[m] >= 0) { f0[d[m]] = s0; f1[d[m]] = s1; f2[d[m]] = s2; }
-}
-
-// Classes completing at the slot's positions of `nwin` (<= GB) consecutive windows, first position pos0,
-// shared out over the NT threads of the slot (t = thread in slot).  The windows are handled together so
-// that one thread has GB independent gathers in flight: the latency chain offsets -> members -> values is
-// paid once per GB elements.
-template <int NT, int GB>
-__device__ __forceinline__ void gs_batch(const KParams2<8>& p, int pos0, int nslots, int nwin, int t) {
-  double *f0 = p.f[0], *f1 = p.f[1], *f2 = p.f[2];
-  int4 b[GB], e[GB];
-#pragma unroll
-  for (int w = 0; w < GB; w++) {
-    if (w < nwin) {
-      b[w] = __ldg(p.gs_eoff + pos0 + w * nslots);
-      e[w] = __ldg(p.gs_eoff + pos0 + w * nslots + 1);
-    } else {
-      b[w] = make_int4(0, 0, 0, 0); e[w] = b[w];
-    }
-  }
-  // pairs (most classes): first NT of every window with all loads of the batch in flight together
-  int2 q[GB];
-  bool ok[GB];
-#pragma unroll
-  for (int w = 0; w < GB; w++) {
-    ok[w] = b[w].x + t < e[w].x;
-    q[w] = make_int2(0, 0);
-    if (ok[w]) q[w] = __ldg(p.gs_pair + b[w].x + t);
-  }
-  double va[GB][3], vb[GB][3];
-#pragma unroll
-  for (int w = 0; w < GB; w++) {
-    if (ok[w]) {
-      va[w][0] = __ldcg(f0 + q[w].x); vb[w][0] = __ldcg(f0 + q[w].y);
-      va[w][1] = __ldcg(f1 + q[w].x); vb[w][1] = __ldcg(f1 + q[w].y);
-      va[w][2] = __ldcg(f2 + q[w].x); vb[w][2] = __ldcg(f2 + q[w].y);
-    }
-  }
-#pragma unroll
-  for (int w = 0; w < GB; w++) {
-    if (ok[w]) {
-      const double s0 = (0.0 + va[w][0]) + vb[w][0], s1 = (0.0 + va[w][1]) + vb[w][1],
-                   s2 = (0.0 + va[w][2]) + vb[w][2];
-      f0[q[w].x] = s0; f0[q[w].y] = s0;
-      f1[q[w].x] = s1; f1[q[w].y] = s1;
-      f2[q[w].x] = s2; f2[q[w].y] = s2;
-    }
-  }
-#pragma unroll 1
-  for (int w = 0; w < nwin; w++) {
-    // (offsets re-read through L1 rather than indexing the register arrays with a run-time index)
-    const int4 bw = __ldg(p.gs_eoff + pos0 + w * nslots), ew = __ldg(p.gs_eoff + pos0 + w * nslots + 1);
-    for (int i = bw.x + t + NT; i < ew.x; i += NT) {      // positions with more than NT pairs
-      const int2 qq = __ldg(p.gs_pair + i);
-      const int d[2] = {qq.x, qq.y};
-      gs_sum_members<2>(f0, f1, f2, d);
-    }
-    for (int i = bw.y + t; i < ew.y; i += NT) {
-      const int4 qq = __ldg(p.gs_quad + i);
-      const int d[4] = {qq.x, qq.y, qq.z, qq.w};
-      gs_sum_members<4>(f0, f1, f2, d);
-    }
-    for (int i = bw.z + t; i < ew.z; i += NT) {
-      const int4 q0 = __ldg(p.gs_oct + 2 * i), q1 = __ldg(p.gs_oct + 2 * i + 1);
-      const int d[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      gs_sum_members<8>(f0, f1, f2, d);
-    }
-    for (int i = bw.w + t; i < ew.w; i += NT) {
-      int d[16];
-#pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int4 qq = __ldg(p.gs_hex + 4 * i + a);
-        d[4 * a] = qq.x; d[4 * a + 1] = qq.y; d[4 * a + 2] = qq.z; d[4 * a + 3] = qq.w;
-      }
-      gs_sum_members<16>(f0, f1, f2, d);
-    }
-  }
-}
-
 // element -> slot map of the XS kernels, shared with the set-up (capi.cu build_xstage): slot s of nslots owns
 // the contiguous run [xs_run_begin(s), xs_run_begin(s + 1)) -- balanced to +-1 element.  (Windows of shorter
 // runs per slot were measured too, r02c/r02f: no faster, and they link fewer faces.)
@@ -223,16 +105,15 @@ __host__ __device__ __forceinline__ bool xs_is_run_start(int e, int nelem, int n
   return (sidx * nelem) / nslots == e;
 }
 
-// GS: compile the in-kernel summation in (FLAG_GS is then honoured); HINT: evict_first policy on the inputs
-template <int NE, int NW, int DS, int NF, int MAXREG, bool GS = false, bool HINT = false, bool LIST = false,
-          int XS = 0>
+// LIST: elements come from p.elem_list (boundary / interior split of a multi-GPU run); XS: x stage (see the header)
+template <int NE, int NW, int DS, int NF, int MAXREG, bool LIST = false, int XS = 0>
 __global__ void __launch_bounds__(V3Cfg<NE, NW, DS, NF>::NTHREADS, 1) __maxnreg__(MAXREG)
 adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   using C = V3Cfg<NE, NW, DS, NF>;
   // XS = 2: lane (g,0) re-loads the previous element's i = 7 value from L2 (__ldcg) and rewrites it -- no cross-lane
   // traffic.  (Tried and dropped, r02c/r02j: the value kept in shared memory or in registers of lane (g,3) and
   // swapped with shfl.xor(3): 4-5 % slower.)
-  static_assert(!XS || (!GS && !LIST), "the x stage runs on contiguous element runs without the in-kernel gs");
+  static_assert(!XS || !LIST, "the x stage runs on contiguous element runs");
   constexpr int LX = 8, N = 512, PLANE = 64;
   constexpr int NPL = LX / NW;        // planes per warp
   constexpr int NTASK = 24;           // (component, j-slab) tasks of the t-direction stages
@@ -260,10 +141,6 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   __syncthreads();
 
   const int nslots = (int)gridDim.x * NE;
-  // inputs are read once: with the in-kernel summation they must not displace f in L2
-  constexpr bool use_hint = HINT;
-  uint64_t pol_stream = 0;
-  if constexpr (HINT) pol_stream = l2_policy_evict_first();
 
   // ========================= consumers ================================================================
   const int slot = tid / C::NSLOT_THR;
@@ -329,51 +206,16 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     uint64_t* full = &wbar[n % DS];
     if (elect_one()) {
       mbar_expect_tx(full, stage_tx);
-      if constexpr (use_hint) tma_load_1d_hint(dst, p.geom + goff * NGEO, NGEO * C::PLANE_BYTES, full, pol_stream);
-      else tma_load_1d(dst, p.geom + goff * NGEO, NGEO * C::PLANE_BYTES, full);
+      tma_load_1d(dst, p.geom + goff * NGEO, NGEO * C::PLANE_BYTES, full);
 #pragma unroll
       for (int a = NGEO; a < NF; a++) {
         const double* src = p.pf[a - NGEO];
-        if (src) {
-          if constexpr (use_hint) tma_load_1d_hint(dst + a * C::PLANE_BYTES, src + goff, C::PLANE_BYTES, full, pol_stream);
-          else tma_load_1d(dst + a * C::PLANE_BYTES, src + goff, C::PLANE_BYTES, full);
-        }
+        if (src) tma_load_1d(dst + a * C::PLANE_BYTES, src + goff, C::PLANE_BYTES, full);
       }
     }
   };
 #pragma unroll
   for (int n = 0; n < DS; n++) issue(n);
-
-  // ---- in-kernel direct-stiffness summation: bookkeeping of this slot ---------------------------------
-  // Windows are published and summed in batches of GSB, the slots of a CTA (and neighbouring CTAs) at
-  // different iterations, so that at most a fraction of the slots is in the latency-bound summation at
-  // any time while the others keep HBM busy.
-  constexpr int GSB = 4;
-  const int st = tid - slot * C::NSLOT_THR;            // thread in slot
-  int gs_pub = 0;                                      // windows [0, gs_pub) of this slot are published
-  int gs_sum = 0;                                      // windows [0, gs_sum) of this slot are summed
-  const int gs_phase = (g0 + (int)blockIdx.x) % GSB;
-  auto gs_publish = [&](int upto) {                    // after the slot barrier that follows the stores
-    if (st == 0) {
-      for (int w = gs_pub; w < upto; w++) red_release_add(p.gs_done + w, 1ull);
-    }
-    gs_pub = upto;
-  };
-  auto gs_sum_upto = [&](int upto) {                   // sum windows [gs_sum, upto)
-    while (gs_sum < upto) {
-      const int nw = (upto - gs_sum < GSB) ? upto - gs_sum : GSB;
-      if (lane == 0) {
-        for (int w = gs_sum; w < gs_sum + nw; w++) {
-          const int rest = p.nelem - w * nslots;
-          const unsigned long long want = (unsigned long long)(rest < nslots ? rest : nslots);
-          while (ld_acquire_u64(p.gs_done + w) < want) __nanosleep(64);
-        }
-      }
-      __syncwarp();
-      gs_batch<C::NSLOT_THR, GSB>(p, g0 + gs_sum * nslots, nslots, nw, st);
-      gs_sum += nw;
-    }
-  };
 
   for (int it = 0; it < n_my; it++) {
     int e;
@@ -524,13 +366,8 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
           Ft[0].x = pv0 * ct; Ft[1].x = pv1 * ct; Ft[2].x = pv2 * ct;
         }
       }
-      if constexpr (use_hint) {
-        if (flags & FLAG_SENS) st_f64x2_hint(p.sens + ebase + qoff, sens2.x, sens2.y, pol_stream);
-        if (flags & FLAG_CHI_OUT) st_f64x2_hint(p.chi_out + ebase + qoff, chi.x, chi.y, pol_stream);
-      } else {
-        if (flags & FLAG_SENS) *reinterpret_cast<double2*>(p.sens + ebase + qoff) = sens2;
-        if (flags & FLAG_CHI_OUT) *reinterpret_cast<double2*>(p.chi_out + ebase + qoff) = chi;
-      }
+      if (flags & FLAG_SENS) *reinterpret_cast<double2*>(p.sens + ebase + qoff) = sens2;
+      if (flags & FLAG_CHI_OUT) *reinterpret_cast<double2*>(p.chi_out + ebase + qoff) = chi;
 
       // t fluxes back to Wt (same locations this lane read gt from), s fluxes to the warp scratch
 #pragma unroll
@@ -604,17 +441,11 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     }
     named_bar_sync(bar_id, C::NSLOT_THR);
 
-    // ---- publish the stored windows / sum the classes that completed gs_lag windows ago --------------------
-    if constexpr (GS) {
-      gs_publish(it + 1);
-      if ((it + gs_phase) % GSB == GSB - 1 && it + 1 - p.gs_lag > gs_sum) gs_sum_upto(it + 1 - p.gs_lag);
-    }
     if constexpr (LIST) {
       e_cur = e_nxt;
       e_nxt = elem_at(it + 2);
     }
   }
-  if constexpr (GS) gs_sum_upto(n_my);
 #undef CT
 }
 

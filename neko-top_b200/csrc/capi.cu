@@ -123,16 +123,14 @@ struct Handle {
   int *d_bnd_elem = nullptr, *d_int_elem = nullptr;
   int nbnd = 0, nint = 0;
 
-  // in-kernel direct-stiffness summation (adjrhs_kernel_v3.cuh FLAG_GS): element processing order and the
+  // class schedule of the pipelined host step / the packed-list pass: element processing order and the
   // class schedule built for it by build_gs_schedule()
   std::vector<int> order;          // processing order of the elements (empty: 0..nelv-1)
   int* d_order = nullptr;
-  int gs_mode = 0;                 // 0: CSR kernels (default, fastest), 1: packed class lists, 2: inside the v3 element kernel
-  int gs_lag = 2;                  // B200_GS_LAG
+  int gs_mode = 0;                 // 0: CSR class lists (default), 1: class lists packed by size (B200_GS_MODE=1)
   bool overlap_elem = false;       // B200_EXCHANGE_OVERLAP=elem: overlap the exchange with the interior-element kernel
   bool exchange_side = false;      // B200_EXCHANGE_SIDE=1: shared-class sum + pack on the communication stream (r02n: no gain)
   int gs_un = 1;                   // classes in flight per thread in gs_op_kernel (B200_GS_UN: 1, 2, 4; measured: 1 is best)
-  bool gs_l2hint = true;           // B200_GS_L2HINT=0: no evict_first policy on the streaming inputs
   bool sched_valid = false;
   int sched_nelem = 0;             // length of the element list the schedule was built for
   int sched_kind = 0;              // 1: all elements (single GPU), 2: interior elements (multi-GPU split)
@@ -140,8 +138,7 @@ struct Handle {
       *sched_hex = nullptr, *sched_left = nullptr;
   int sched_nleft = 0;
   int sched_n2 = 0, sched_n4 = 0, sched_n8 = 0, sched_n16 = 0;
-  int64_t sched_nfused = 0;        // classes summed inside the element kernel
-  unsigned long long* sched_done = nullptr;
+  int64_t sched_nfused = 0;        // classes in the packed lists (2..16 members)
   std::vector<int> sched_elem_last;   // host copy: per position, the last position whose classes touch it (kind 1)
 
   // x stage of the lx = 8 element kernel (adjrhs_kernel_v3.cuh XS): per-element link flags and the CSR lists
@@ -206,7 +203,6 @@ struct LaunchArgs {
   int elem_begin;         // used only when elem_list == nullptr (via pointer offsets)
   bool sources;
   bool no_dealias;         // un-fused GLL-grid drop-in: ignore the handle's dealias switch
-  bool gs_in_kernel;       // sum the node classes inside the element kernel (needs a valid schedule)
   bool xstage;             // v3 XS: contiguous runs per slot, i-face pair classes summed in the kernel
 };
 
@@ -329,35 +325,13 @@ int fill_params2_lx8(Handle* h, const LaunchArgs& a, KParams2<8>& p) {
       return fail(B200_ERR_STATE, "internal: x stage without matching link flags");
     p.xmask = h->xs_mask[0];
   }
-  if (a.gs_in_kernel) {
-    if (!h->sched_valid || a.elem_begin != 0 || a.nelem != h->sched_nelem)
-      return fail(B200_ERR_STATE, "internal: in-kernel gs without a matching schedule");
-    p.flags |= FLAG_GS;
-    p.gs_eoff = reinterpret_cast<const int4*>(h->sched_eoff);
-    p.gs_pair = reinterpret_cast<const int2*>(h->sched_pair);
-    p.gs_quad = reinterpret_cast<const int4*>(h->sched_quad);
-    p.gs_oct = reinterpret_cast<const int4*>(h->sched_oct);
-    p.gs_hex = reinterpret_cast<const int4*>(h->sched_hex);
-    p.gs_done = h->sched_done;
-    p.gs_lag = h->gs_lag;
-  }
   return B200_OK;
 }
 
 constexpr int XS_NE = 3;   // element slots per CTA of the x-stage kernels (the default configuration)
-template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST, int XS = 0>
-int launch_v3_cfg2(Handle* h, const LaunchArgs& a);
-
-template <int NE, int NW, int DS, int NF, int MAXREG, bool GS = false, bool HINT = false>
-int launch_v3_cfg(Handle* h, const LaunchArgs& a) {
-  if (a.elem_list) return launch_v3_cfg2<NE, NW, DS, NF, MAXREG, GS, HINT, true>(h, a);
-  return launch_v3_cfg2<NE, NW, DS, NF, MAXREG, GS, HINT, false>(h, a);
-}
-
-template <int NE, int NW, int DS, int NF, int MAXREG, bool GS, bool HINT, bool LIST, int XS>
+template <int NE, int NW, int DS, int NF, int MAXREG, bool LIST, int XS = 0>
 int launch_v3_cfg2(Handle* h, const LaunchArgs& a) {
   using C = V3Cfg<NE, NW, DS, NF>;
-  if (a.gs_in_kernel != GS) return fail(B200_ERR_STATE, "internal: v3 kernel variant / gs_in_kernel mismatch");
   if (a.xstage != (XS != 0)) return fail(B200_ERR_STATE, "internal: v3 kernel variant / x stage mismatch");
   constexpr int SMEM = C::SMEM;
   static_assert(SMEM <= 227 * 1024, "v3 configuration exceeds the shared memory of an SM");
@@ -365,7 +339,7 @@ int launch_v3_cfg2(Handle* h, const LaunchArgs& a) {
   static_assert(C::NTHREADS * MAXREG <= 65536, "v3 configuration exceeds the register file");
   KParams2<8> p;
   if (int r = fill_params2_lx8<NF>(h, a, p)) return r;
-  auto kern = adjrhs_v3_kernel<NE, NW, DS, NF, MAXREG, GS, HINT, LIST, XS>;
+  auto kern = adjrhs_v3_kernel<NE, NW, DS, NF, MAXREG, LIST, XS>;
   static unsigned long long attr_set = 0;   // per instantiation, one bit per device (the attribute is per device)
   if (h->device >= 64 || !(attr_set >> h->device & 1ull)) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -374,44 +348,33 @@ int launch_v3_cfg2(Handle* h, const LaunchArgs& a) {
   const int grid = std::min((a.nelem + NE - 1) / NE, h->num_sm);
   if (grid < 1) return B200_OK;
   if (XS && grid * NE != h->xs_nslots) return fail(B200_ERR_STATE, "internal: x-stage links built for another grid");
-  if (a.gs_in_kernel) {
-    // one completion counter per window of grid*NE positions; the spin-wait needs every CTA resident
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHREADS, C::SMEM));
-    if (per_sm < 1) return fail(B200_ERR_STATE, "v3 kernel does not fit on an SM");
-    const int nwin = (a.nelem + grid * NE - 1) / (grid * NE);
-    CK(cudaMemsetAsync(h->sched_done, 0, sizeof(unsigned long long) * nwin, h->stream));
-  }
   kern<<<grid, C::NTHREADS, SMEM, h->stream>>>(p);
   LAUNCHED();
   CK(cudaGetLastError());
   return B200_OK;
 }
 
+template <int NE, int NW, int DS, int NF, int MAXREG>
+int launch_v3_cfg(Handle* h, const LaunchArgs& a) {
+  if (a.elem_list) return launch_v3_cfg2<NE, NW, DS, NF, MAXREG, true>(h, a);
+  return launch_v3_cfg2<NE, NW, DS, NF, MAXREG, false>(h, a);
+}
+
 template <int NE, int NW, int DS, int MAXREG, int NE_FULL = NE, int DS_FULL = DS>
 int launch_v3(Handle* h, const LaunchArgs& a) {
-  if (a.gs_in_kernel) return fail(B200_ERR_STATE, "internal: this v3 configuration has no in-kernel gs variant");
   if (a.fs[0] || a.fin[0]) return launch_v3_cfg<NE_FULL, NW, DS_FULL, NF_FULL, MAXREG>(h, a);
   return launch_v3_cfg<NE, NW, DS, NF_FUSED, MAXREG>(h, a);
 }
-// the default configuration: also built with the in-kernel direct-stiffness summation
+// the default configuration (with or without the x stage)
 int launch_v3_default(Handle* h, const LaunchArgs& a) {
   const bool full = a.fs[0] || a.fin[0];
   if (a.xstage) {
-    if (a.gs_in_kernel || a.elem_list) return fail(B200_ERR_STATE, "internal: x stage with in-kernel gs / element list");
-    if (full) return launch_v3_cfg2<XS_NE, 4, 1, NF_FULL, 168, false, false, false, 2>(h, a);
-    return launch_v3_cfg2<XS_NE, 4, 2, NF_FUSED, 168, false, false, false, 2>(h, a);
+    if (a.elem_list) return fail(B200_ERR_STATE, "internal: x stage with an element list");
+    if (full) return launch_v3_cfg2<XS_NE, 4, 1, NF_FULL, 168, false, 2>(h, a);
+    return launch_v3_cfg2<XS_NE, 4, 2, NF_FUSED, 168, false, 2>(h, a);
   }
-  if (!a.gs_in_kernel) {
-    if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168>(h, a);
-    return launch_v3_cfg<3, 4, 2, NF_FUSED, 168>(h, a);
-  }
-  if (h->gs_l2hint) {
-    if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168, true, true>(h, a);
-    return launch_v3_cfg<3, 4, 2, NF_FUSED, 168, true, true>(h, a);
-  }
-  if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168, true, false>(h, a);
-  return launch_v3_cfg<3, 4, 2, NF_FUSED, 168, true, false>(h, a);
+  if (full) return launch_v3_cfg<3, 4, 1, NF_FULL, 168>(h, a);
+  return launch_v3_cfg<3, 4, 2, NF_FUSED, 168>(h, a);
 }
 
 // fine-grid operators (advop_kernel.cuh): dealiased adjoint / linearised advection, GLL-grid linearised
@@ -480,11 +443,8 @@ int launch_fused(Handle* h, const LaunchArgs& a) {
     case 8:
       switch (cfg) {
         case 3: return launch_v2<8, 3, 4, 255, 3, 4>(h, a);   // the DFMA (v2) kernel at lx = 8, for A/B runs
-        case 20: return launch_v3<4, 4, 1, 128, 3, 1>(h, a); // 16 warps, 184 KB
-        case 21: return launch_v3<3, 4, 2, 168, 3, 1>(h, a); // 12 warps, 222 KB
-        case 22: return launch_v3<2, 8, 1, 128>(h, a);       // 16 warps, 1 plane per warp
-        case 23: return launch_v3<6, 2, 1, 168>(h, a);       // 12 warps, 4 planes per warp
-        case 25: return launch_v3<3, 4, 1, 168>(h, a);       // 12 warps, 138 KB
+        case 20: return launch_v3<4, 4, 1, 128, 3, 1>(h, a); // 16 warps (A/B runs, profiles r01c)
+        case 25: return launch_v3<3, 4, 1, 168>(h, a);       // 12 warps, one plane stage
         default: return launch_v3_default(h, a);
       }
     // (two producer warps at lx = 7, 9, 10: -3 % / 0 / +3 %, r02n: these orders are bound by the consumers)
@@ -627,20 +587,20 @@ int dmalloc(T** p, size_t count) {
   return B200_OK;
 }
 
-// true if launch_fused() will run the v3 element kernel (the one that can sum node classes itself)
+// true if launch_fused() will run the default v3 element kernel (the one with an x-stage variant)
 bool uses_v3(const Handle* h) {
   return h->lx == 8 && !h->dealias_fused && (h->cfg <= 0 || (h->cfg > 25 && h->cfg < 100));   // default config
 }
 
 void free_schedule(Handle* h) {
   cudaFree(h->sched_eoff); cudaFree(h->sched_pair); cudaFree(h->sched_quad); cudaFree(h->sched_oct);
-  cudaFree(h->sched_hex); cudaFree(h->sched_left); cudaFree(h->sched_done);
+  cudaFree(h->sched_hex); cudaFree(h->sched_left);
   h->sched_eoff = h->sched_pair = h->sched_quad = h->sched_oct = h->sched_hex = h->sched_left = nullptr;
-  h->sched_done = nullptr;
   h->sched_valid = false; h->sched_nleft = 0; h->sched_nfused = 0; h->sched_nelem = 0; h->sched_kind = 0;
 }
 
-// Class schedule of the in-kernel direct-stiffness summation for the element list (list, nlist)
+// Class schedule (classes sorted by the position of the element that completes them, packed by size) for the element list (list, nlist):
+// what the pipelined host step and the packed-list pass walk
 // (list == nullptr: elements 0..nlist-1 in order).  Elements outside the list count as already stored.
 int build_gs_schedule(Handle* h, const int* list, int nlist) {
   free_schedule(h);
@@ -690,7 +650,6 @@ int build_gs_schedule(Handle* h, const int* list, int nlist) {
     LAUNCHED();
     CK(cudaGetLastError());
   }
-  if (int r = dmalloc(&h->sched_done, (size_t)nlist + 1)) return r;
   h->sched_elem_last.clear();
   if (!list && nlist == h->nelv) {          // mesh order: what the pipelined host step needs
     int* d_last = nullptr;
@@ -907,7 +866,7 @@ int gs_packed(Handle* h, double* f0, double* f1, double* f2) {
   return gs_packed_range(h, f0, f1, f2, lo, hi);
 }
 
-// classes with more than 16 members are not in the in-kernel schedule
+// classes with more than 16 members are not in the packed lists
 int gs_leftover(Handle* h, double* f0, double* f1, double* f2) {
   if (h->sched_nleft == 0) return B200_OK;
   const int threads = 256, grid = grid_for(h->sched_nleft, threads, h->num_sm, 4);
@@ -937,7 +896,6 @@ LaunchArgs make_args(const void* vx, const void* vy, const void* vz, const void*
   a.nelem = nelv;
   a.elem_begin = 0;
   a.no_dealias = false;
-  a.gs_in_kernel = false;
   a.xstage = false;
   return a;
 }
@@ -1003,10 +961,8 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   h->num_sm = prop.multiProcessorCount;
   const char* c = getenv("B200_ADJRHS_CFG");
   h->cfg = c ? atoi(c) : -1;
-  const char* g = getenv("B200_GS_FUSED");
-  if (g) h->gs_mode = atoi(g) != 0 ? 2 : 0;
-  g = getenv("B200_GS_MODE");
-  if (g) h->gs_mode = std::min(2, std::max(0, atoi(g)));
+  const char* g = getenv("B200_GS_MODE");
+  if (g) h->gs_mode = atoi(g) != 0 ? 1 : 0;
   g = getenv("B200_EXCHANGE_OVERLAP");
   if (g) h->overlap_elem = (strcmp(g, "elem") == 0);
   g = getenv("B200_EXCHANGE_SIDE");
@@ -1015,10 +971,6 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   if (g) h->phase_timing = atoi(g) != 0;
   g = getenv("B200_GS_UN");
   if (g) h->gs_un = atoi(g);
-  g = getenv("B200_GS_LAG");
-  if (g) h->gs_lag = std::max(1, atoi(g));
-  g = getenv("B200_GS_L2HINT");
-  if (g) h->gs_l2hint = atoi(g) != 0;
   g = getenv("B200_XSTAGE");
   if (g) h->xs_enable = std::min(2, std::max(0, atoi(g)));
   g = getenv("B200_XS_NOLINK");
@@ -1201,12 +1153,11 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
   const bool split = mgpu && h->nbnd > 0;
   // direct-stiffness summation inside the element kernel (v3, lx = 8) while f is still in L2; the masked
   // lube term is applied by a separate kernel after the element kernel, so it keeps the separate gs pass
-  // gs_mode 2: summation inside the v3 element kernel; 1: separate pass over the packed class lists of the
+  // gs_mode 1: separate pass over the packed class lists of the
   // schedule; 0: the CSR kernels.  Without a boundary/interior split a communicator needs the CSR pass
   // (it sums the shared classes too, before the exchange).
   int mode = h->gs_mode;
   if (h->nclass == 0 || (!split && h->comm && h->nshared > 0)) mode = 0;
-  if (mode == 2 && (!uses_v3(h) || masked_lube || (split && h->nint == 0))) mode = 1;
   if (mode > 0) {
     const int kind = split ? 2 : 1;
     if (!h->sched_valid || h->sched_kind != kind) {
@@ -1215,7 +1166,6 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     }
     if (!h->sched_valid) mode = 0;
   }
-  const bool fuse_gs = (mode == 2);
   if (split) {
     // boundary elements first, their shared nodes summed locally, packed and sent while the interior
     // elements are computed
@@ -1236,13 +1186,11 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     if (int r = phase_mark(h, 2)) return r;
     if (int r = gs_exchange(h, f0, f1, f2, 3)) return r;
     if (int r = phase_mark(h, 3)) return r;
-    LaunchArgs ai = a; ai.elem_list = h->d_int_elem; ai.nelem = h->nint; ai.gs_in_kernel = fuse_gs;
+    LaunchArgs ai = a; ai.elem_list = h->d_int_elem; ai.nelem = h->nint;
     if (h->nint > 0 && !masked_lube) if (int r = launch_fused(h, ai)) return r;
     if (int r = phase_mark(h, 4)) return r;
     if (int r = time_mark(h)) return r;
-    if (mode == 2) {
-      if (int r = gs_leftover(h, f0, f1, f2)) return r;
-    } else if (mode == 1) {
+    if (mode == 1) {
       if (int r = gs_packed(h, f0, f1, f2)) return r;
       if (int r = gs_leftover(h, f0, f1, f2)) return r;
     } else if (h->nclass > 0) {
@@ -1256,14 +1204,12 @@ int b200_adjrhs_step(void* handle, const void* vx, const void* vy, const void* v
     if (int r = gs_finish_exchange(h, f0, f1, f2, 3)) return r;
     if (int r = phase_mark(h, 6)) return r;
   } else {
-    a.elem_list = h->d_order; a.gs_in_kernel = fuse_gs;
+    a.elem_list = h->d_order;
     a.xstage = xs && mode == 0;
     if (int r = launch_fused(h, a)) return r;
     if (int r = masked_lube_post(h, a)) return r;
     if (int r = time_mark(h)) return r;
-    if (mode == 2) {
-      if (int r = gs_leftover(h, f0, f1, f2)) return r;
-    } else if (mode == 1) {
+    if (mode == 1) {
       if (int r = gs_packed(h, f0, f1, f2)) return r;
       if (int r = gs_leftover(h, f0, f1, f2)) return r;
     } else if (a.xstage) {
@@ -1308,15 +1254,15 @@ int b200_adjrhs_set_element_order(void* handle, const int* nelem, const int* ord
 
 int b200_adjrhs_set_gs_fused(void* handle, const int* flag) {
   if (!handle || !flag) return fail(B200_ERR_ARG, "set_gs_fused: null argument");
-  H(handle)->gs_mode = (*flag > 0) ? 2 : (*flag < 0 ? 1 : 0);
+  H(handle)->gs_mode = (*flag != 0) ? 1 : 0;
   return B200_OK;
 }
 
 int b200_adjrhs_gs_info(void* handle, int* fused, int64_t* classes_in_kernel, int64_t* classes_total) {
   if (!handle) return fail(B200_ERR_ARG, "null handle");
   Handle* h = H(handle);
-  if (fused) *fused = (h->sched_valid && h->gs_mode == 2) ? 1 : 0;
-  if (classes_in_kernel) *classes_in_kernel = h->sched_valid ? h->sched_nfused : 0;
+  if (fused) *fused = 0;       // the in-kernel class summation of round 1 is gone (superseded by the staged summation)
+  if (classes_in_kernel) *classes_in_kernel = (h->sched_valid && h->gs_mode == 1) ? h->sched_nfused : 0;
   if (classes_total) *classes_total = h->nclass;
   return B200_OK;
 }

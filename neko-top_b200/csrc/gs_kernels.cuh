@@ -217,7 +217,7 @@ __global__ void gs_op_list_kernel(double* f0, double* f1, double* f2,
     }
   }
 }
-// ---- schedule of the in-kernel direct-stiffness summation (adjrhs_kernel_v3.cuh, FLAG_GS) ------------------
+// ---- class schedule: classes sorted by completing element position, packed by size (pipelined host step, gs mode 1) ----
 // pos[e] = position of element e in the processing list (-1: not in the list == stored before the launch)
 __global__ void gs_pos_kernel(const int* __restrict__ order, int norder, int* __restrict__ pos) {
   const int stride = gridDim.x * blockDim.x;

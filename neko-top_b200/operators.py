@@ -528,16 +528,12 @@ class fused_adjoint_rhs_t:
         o = np.ascontiguousarray(order, dtype=np.int32)
         check(_lib.lib().b200_adjrhs_set_element_order(self._hd.h, _ci(o.size), o.ctypes.data_as(C.POINTER(C.c_int))))
 
-    def set_gs_fused(self, flag=True):
-        """True: sum the node classes inside the v3 element kernel (experimental); False: separate CSR pass."""
-        self.set_gs_mode(2 if flag else 0)
-
     def set_gs_mode(self, mode):
-        """0: separate CSR pass (default), 1: separate pass over the packed class lists, 2: inside the element kernel."""
-        check(_lib.lib().b200_adjrhs_set_gs_fused(self._hd.h, _ci({2: 1, 1: -1, 0: 0}[int(mode)])))
+        """Class-list pass when the staged summation is not in use: 0 = CSR lists (default), 1 = lists packed by size."""
+        check(_lib.lib().b200_adjrhs_set_gs_fused(self._hd.h, _ci(1 if int(mode) else 0)))
 
     def gs_info(self):
-        """(fused, classes summed inside the element kernel, classes in total)."""
+        """(0, classes in the packed lists when in use, classes in total)."""
         a, b, c = C.c_int(0), C.c_int64(0), C.c_int64(0)
         check(_lib.lib().b200_adjrhs_gs_info(self._hd.h, C.byref(a), C.byref(b), C.byref(c)))
         return bool(a.value), b.value, c.value

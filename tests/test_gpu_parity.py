@@ -361,10 +361,10 @@ def _check_step_host(op, v, ub, rho, f, sens):
 
 
 @pytest.mark.parametrize("order_kind", ["mesh", "tile", "random"])
-def test_step_gs_in_kernel(oracle, order_kind):
-    """lx = 8: b200_adjrhs_step sums the node classes inside the element kernel (several windows of
-    element slots, any processing order).  Against the oracle <= 1e-12 and BIT-identical to the separate
-    gather-scatter pass; repeated steps reuse the schedule."""
+def test_step_gs_packed_lists(oracle, order_kind):
+    """lx = 8: b200_adjrhs_step with the class lists packed by size and sorted by completing element (gs mode 1: the
+    lists the pipelined host step walks), any processing order.  Against the oracle <= 1e-12 and BIT-identical to
+    the CSR pass; repeated steps reuse the schedule."""
     from neko_top_b200 import workloads
     lx = 8
     P = Problem(lx, ne=(12, 10, 9), deform=0.02)      # 1080 elements = 3 windows of 444 slots
@@ -380,20 +380,19 @@ def test_step_gs_in_kernel(oracle, order_kind):
         op.set_element_order(np.random.default_rng(3).permutation(P.nelv))
     v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
     f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
-    op.set_gs_mode(2)
+    op.set_gs_mode(1)
     for _ in range(3):
         op.step(v, ub, f, rho=rho, sens=sens)
     fused, nin, ntot = op.gs_info()
-    assert fused and nin == ntot > 0
+    assert not fused and nin == ntot > 0
     for c in range(3):
         assert rel_l2(f[c].cpu().numpy(), ref[c]) <= TOL
     assert rel_l2(sens.cpu().numpy(), so) <= TOL
-    for mode in (1, 0):        # packed class lists (the default), CSR kernels
-        op.set_gs_mode(mode)
-        g = [_nan(P.n) for _ in range(3)]
-        op.step(v, ub, g, rho=rho)
-        for c in range(3):
-            assert torch.equal(f[c], g[c]), f"gs mode 2 and mode {mode} must be bit-identical"
+    op.set_gs_mode(0)          # CSR class lists
+    g = [_nan(P.n) for _ in range(3)]
+    op.step(v, ub, g, rho=rho)
+    for c in range(3):
+        assert torch.equal(f[c], g[c]), "packed-list and CSR passes must be bit-identical"
     _check_step_host(op, v, ub, rho, f, sens)
     op.free()
 
@@ -495,7 +494,7 @@ def test_step_xstage(oracle, kind):
     op.free()
 
 
-def test_step_gs_in_kernel_irregular_classes(oracle):
+def test_step_gs_packed_lists_irregular_classes(oracle):
     """Node classes of every size (3, 5..16 members and > 16, which stay with the list kernel): keys of a
     box mesh folded modulo a small number so that unrelated nodes are identified."""
     lx = 8
@@ -517,18 +516,17 @@ def test_step_gs_in_kernel_irregular_classes(oracle):
     assert gnc == nc and np.array_equal(gcid, cid)
     v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
     f = [_nan(P.n) for _ in range(3)]
-    op.set_gs_mode(2)
+    op.set_gs_mode(1)
     op.step(v, ub, f, rho=rho)
     fused, nin, ntot = op.gs_info()
-    assert fused and 0 < nin < ntot
+    assert not fused and 0 < nin < ntot
     for c in range(3):
         assert rel_l2(f[c].cpu().numpy(), oracle.gs_add(fo[c], cid, nc)) <= TOL
-    for mode in (1, 0):
-        op.set_gs_mode(mode)
-        g = [_nan(P.n) for _ in range(3)]
-        op.step(v, ub, g, rho=rho)
-        for c in range(3):
-            assert torch.equal(f[c], g[c])
+    op.set_gs_mode(0)
+    g = [_nan(P.n) for _ in range(3)]
+    op.step(v, ub, g, rho=rho)
+    for c in range(3):
+        assert torch.equal(f[c], g[c])
     _check_step_host(op, v, ub, rho, f, None)
     op.free()
 
@@ -581,7 +579,7 @@ def test_edge_cases(oracle):
         cid, nc = oracle.gs_classes(P.keys.reshape(-1).numpy())
         op = sp_ops(P)
         op.gs.init(P.keys.reshape(-1).cuda())
-        for mode in (0, 2):
+        for mode in (0, 1):
             op.set_gs_mode(mode)
             f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
             op.step(P.cuda("v"), P.cuda("ub"), f, rho=P.cuda("rho"), sens=sens)

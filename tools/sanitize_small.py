@@ -21,7 +21,7 @@ for lx in (5, 6, 8):
     v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
     f = [torch.zeros(P.n, device="cuda", dtype=torch.float64) for _ in range(3)]
     sens = torch.zeros(P.n, device="cuda", dtype=torch.float64)
-    for mode in ((0, 1, 2) if lx == 8 else (0, 1)):
+    for mode in (0, 1):
         op.set_gs_mode(mode)
         op.step(v, ub, f, rho=rho, sens=sens)
     op.set_gs_mode(0)

@@ -69,31 +69,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-// same with an L2 eviction-priority hint (createpolicy handle)
-__device__ __forceinline__ void tma_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
-                                                 uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void st_f64x2_hint(double* addr, double a, double b, uint64_t policy) {
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(addr), "d"(a), "d"(b), "l"(policy)
-               : "memory");
-}
-// 8-byte Ampere-style async copy (SASS: LDGSTS) + deferred arrive, for odd LX
-__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

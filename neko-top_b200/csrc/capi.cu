@@ -587,6 +587,25 @@ int dmalloc(T** p, size_t count) {
   return B200_OK;
 }
 
+// frees device temporaries on every exit path of a set-up routine
+struct DevTemps {
+  std::vector<void*> ptrs;
+  ~DevTemps() { for (void* q : ptrs) cudaFree(q); }
+  template <typename T>
+  int alloc(T** q, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(q), std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "cudaMalloc of a set-up buffer failed: %s", cudaGetErrorString(e));
+    ptrs.push_back(*q);
+    return B200_OK;
+  }
+  // free one buffer early (peak memory of the set-up) and forget it
+  template <typename T>
+  void release(T*& q) {
+    for (auto& x : ptrs) if (x == (void*)q) { cudaFree(x); x = nullptr; }
+    q = nullptr;
+  }
+};
+
 // true if launch_fused() will run the default v3 element kernel (the one with an x-stage variant)
 bool uses_v3(const Handle* h) {
   return h->lx == 8 && !h->dealias_fused && (h->cfg <= 0 || (h->cfg > 25 && h->cfg < 100));   // default config
@@ -697,19 +716,6 @@ void free_xstage(Handle* h) {
   h->xs_off = h->xs_dof = nullptr; h->xs_skip = nullptr;
   h->xs_valid = false; h->xs_nclass = 0; h->xs_nslots = 0; h->xs_nlinked = 0; h->xs_nmember = 0; h->xs_level = 0;
 }
-
-// frees device temporaries on every exit path of a set-up routine
-struct DevTemps {
-  std::vector<void*> ptrs;
-  ~DevTemps() { for (void* q : ptrs) cudaFree(q); }
-  template <typename T>
-  int alloc(T** q, size_t count) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(q), std::max<size_t>(count, 1) * sizeof(T));
-    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "cudaMalloc of a set-up buffer failed: %s", cudaGetErrorString(e));
-    ptrs.push_back(*q);
-    return B200_OK;
-  }
-};
 
 // Staged direct-stiffness summation (gs_kernels.cuh "staged"): per-element face masks / neighbours and the CSR
 // lists of the classes left to the class-list pass.  Needs gs_init (and gs_init_shared, if any) done.
@@ -1830,62 +1836,67 @@ int b200_gs_init(void* handle, const int64_t* key, const int* on_device) {
   free_shared(h);      // the shared-node lists index the old class list: b200_gs_init_shared must be called again
   if (n == 0) { h->nclass = 0; h->nmember = 0; h->have_gs = true; return B200_OK; }
 
-  int64_t *d_key_in = nullptr, *d_key = nullptr, *d_comp = nullptr, *d_comp2 = nullptr;
+  // every temporary lives in T: freed early where the peak matters, and on every error return
+  DevTemps T;
+  int64_t *d_key_in = nullptr, *d_key_own = nullptr, *d_key = nullptr, *d_comp = nullptr, *d_comp2 = nullptr;
   int *d_idx = nullptr, *d_dof = nullptr, *d_head = nullptr, *d_hscan = nullptr;
   unsigned char* d_shared = nullptr;
-  void* d_tmp = nullptr;
+  unsigned char* d_tmp = nullptr;
   size_t tmp_bytes = 0;
   if (on_device && *on_device) d_key_in = const_cast<int64_t*>(key);
   else {
-    if (int r = dmalloc(&d_key_in, n)) return r;
+    if (int r = T.alloc(&d_key_own, n)) return r;
+    d_key_in = d_key_own;
     CK(cudaMemcpyAsync(d_key_in, key, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
   }
-  if (int r = dmalloc(&d_key, n)) return r;
-  if (int r = dmalloc(&d_idx, n)) return r;
-  if (int r = dmalloc(&d_dof, n)) return r;
+  if (int r = T.alloc(&d_key, n)) return r;
+  if (int r = T.alloc(&d_idx, n)) return r;
+  if (int r = T.alloc(&d_dof, n)) return r;
   const int threads = 256;
   const int grid = grid_for(n, threads, h->num_sm, 8);
   gs_iota_kernel<<<grid, threads, 0, st>>>(d_idx, n);
   LAUNCHED();
   // 1. stable radix sort of (key, dof)
   CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key_in, d_key, d_idx, d_dof, n, 0, 64, st));
-  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  if (int r = T.alloc(&d_tmp, tmp_bytes)) return r;
   CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key_in, d_key, d_idx, d_dof, n, 0, 64, st));
-  CK(cudaFree(d_tmp)); d_tmp = nullptr;
-  if (!(on_device && *on_device)) { CK(cudaStreamSynchronize(st)); CK(cudaFree(d_key_in)); }
+  CK(cudaStreamSynchronize(st));
+  T.release(d_tmp);
+  T.release(d_key_own);
   // 2. mark shared members and run heads
-  if (int r = dmalloc(&d_shared, n)) return r;
-  if (int r = dmalloc(&d_head, n)) return r;
-  if (int r = dmalloc(&d_hscan, n)) return r;
+  if (int r = T.alloc(&d_shared, n)) return r;
+  if (int r = T.alloc(&d_head, n)) return r;
+  if (int r = T.alloc(&d_hscan, n)) return r;
   gs_mark_kernel<<<grid, threads, 0, st>>>(d_key, n, d_shared, d_head);
   LAUNCHED();
   CK(cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, d_head, d_hscan, cub::Max(), n, st));
-  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  if (int r = T.alloc(&d_tmp, tmp_bytes)) return r;
   CK(cub::DeviceScan::InclusiveScan(d_tmp, tmp_bytes, d_head, d_hscan, cub::Max(), n, st));
-  CK(cudaFree(d_tmp)); d_tmp = nullptr;
+  CK(cudaStreamSynchronize(st));
+  T.release(d_tmp);
   // 3. composite keys (first dof of class, dof) and rep[]
-  CK(cudaFree(d_key)); d_key = nullptr;
-  if (int r = dmalloc(&d_comp, n)) return r;
+  T.release(d_key);
+  if (int r = T.alloc(&d_comp, n)) return r;
   if (int r = dmalloc(&h->gs_rep, n)) return r;
   gs_compose_kernel<<<grid, threads, 0, st>>>(d_dof, d_hscan, n, d_comp, h->gs_rep);
   LAUNCHED();
-  CK(cudaFree(d_head)); CK(cudaFree(d_hscan)); CK(cudaFree(d_idx));
+  CK(cudaStreamSynchronize(st));
+  T.release(d_head); T.release(d_hscan); T.release(d_idx);
   // 4. keep shared members only
   int64_t* d_ns = nullptr;
-  if (int r = dmalloc(&d_ns, 1)) return r;
-  if (int r = dmalloc(&d_comp2, n)) return r;
+  if (int r = T.alloc(&d_ns, 1)) return r;
+  if (int r = T.alloc(&d_comp2, n)) return r;
   CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_comp, d_shared, d_comp2, d_ns, n, st));
-  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  if (int r = T.alloc(&d_tmp, tmp_bytes)) return r;
   CK(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_comp, d_shared, d_comp2, d_ns, n, st));
-  CK(cudaFree(d_tmp)); d_tmp = nullptr;
   int64_t ns = 0;
   CK(cudaMemcpyAsync(&ns, d_ns, sizeof ns, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  CK(cudaFree(d_shared)); CK(cudaFree(d_dof));
+  T.release(d_tmp);
+  T.release(d_shared); T.release(d_dof);
   h->nmember = ns;
   if (ns == 0) {
     h->nclass = 0;
-    CK(cudaFree(d_comp)); CK(cudaFree(d_comp2)); CK(cudaFree(d_ns));
     if (int r = dmalloc(&h->gs_off, 1)) return r;
     if (int r = dmalloc(&h->gs_dof, 1)) return r;
     h->have_gs = true;
@@ -1893,24 +1904,24 @@ int b200_gs_init(void* handle, const int64_t* key, const int* on_device) {
   }
   // 5. order members by (first dof of class, dof): element-surface order
   CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_comp2, d_comp, ns, 0, 64, st));
-  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  if (int r = T.alloc(&d_tmp, tmp_bytes)) return r;
   CK(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_comp2, d_comp, ns, 0, 64, st));
-  CK(cudaFree(d_tmp)); d_tmp = nullptr;
-  CK(cudaFree(d_comp2));
+  CK(cudaStreamSynchronize(st));
+  T.release(d_tmp);
+  T.release(d_comp2);
   unsigned char* d_h2 = nullptr;
   if (int r = dmalloc(&h->gs_dof, ns)) return r;
-  if (int r = dmalloc(&d_h2, ns)) return r;
+  if (int r = T.alloc(&d_h2, ns)) return r;
   const int grid2 = grid_for(ns, threads, h->num_sm, 8);
   gs_split_kernel<<<grid2, threads, 0, st>>>(d_comp, ns, h->gs_dof, d_h2);
   LAUNCHED();
   // 6. class offsets = positions of heads (+ terminator)
   int* d_off_tmp = nullptr;
-  if (int r = dmalloc(&d_off_tmp, ns + 1)) return r;
+  if (int r = T.alloc(&d_off_tmp, ns + 1)) return r;
   thrust::counting_iterator<int> cnt(0);
   CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, cnt, d_h2, d_off_tmp, d_ns, ns, st));
-  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  if (int r = T.alloc(&d_tmp, tmp_bytes)) return r;
   CK(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, cnt, d_h2, d_off_tmp, d_ns, ns, st));
-  CK(cudaFree(d_tmp)); d_tmp = nullptr;
   int64_t nc = 0;
   CK(cudaMemcpyAsync(&nc, d_ns, sizeof nc, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1920,7 +1931,6 @@ int b200_gs_init(void* handle, const int64_t* key, const int* on_device) {
   const int ns_i = (int)ns;
   CK(cudaMemcpyAsync(h->gs_off + nc, &ns_i, sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
-  CK(cudaFree(d_off_tmp)); CK(cudaFree(d_h2)); CK(cudaFree(d_comp)); CK(cudaFree(d_ns));
   h->have_gs = true;
   return B200_OK;
 }

@@ -69,6 +69,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// 8-byte Ampere-style asynchronous copy global -> shared (SASS: LDGSTS), completion by cp.async.wait_*
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

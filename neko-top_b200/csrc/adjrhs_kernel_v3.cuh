@@ -29,15 +29,16 @@
 // (packed geometry image + point-wise fields) of the plane it will need DS planes later.
 // Arithmetic = adjrhs_common.cuh header.
 //
-// XS ("x stage", profiles/README.md r02): the separate gather-scatter pass re-reads and re-writes ALL of f because
-// every 32-byte sector of an element holds a node of an i-face (i = 0 or 7).  With XS each slot processes runs of
-// consecutive elements, and where element e-1 and e are glued i=7 -> i=0 with identical (j,k) orientation
-// (p.xlink[e], verified against the gather-scatter classes at set-up) the 36 face-interior pair classes are
-// summed here: before its regular 128-bit store, lane (g,0) re-loads the previous element's i = 7 value of its
-// row (stored one iteration earlier by lane (g,3): an L2 hit, __ldcg), adds it to its own i = 0 value and
-// rewrites the partner with the same sum (8-byte store into a line that is still in L2).  a + b is
-// commutative, so both copies are bit-identical to the oracle's (0 + a) + b.  The pass that follows skips
-// these classes and then touches only the rows j = 0,7 / planes k = 0,7: 44 % of the sectors.
+// XS ("x stage" of the staged direct-stiffness summation, gs_kernels.cuh "staged", profiles/README.md r02): the
+// class-list pass re-reads and re-writes ALL of f because every 32-byte sector of an element holds a node of an
+// i-face (i = 0 or 7).  With XS each slot processes a contiguous run of elements, and for every node (0,j,k) of
+// element e whose bit (j + 8k) is set in p.xmask[e] -- proven at set-up to pair with node (7,j,k) of element e-1,
+// the slot's previous element -- the pair is summed here: lane (g,0) fetches the partner value (stored one
+// iteration earlier by lane (g,3), an L2 hit) with an asynchronous copy into the warp's scratch, adds it to its
+// own i = 0 value before the regular 128-bit store and rewrites the partner with the same sum (8-byte store into a
+// line that is still in L2: the kernel's DRAM traffic does not change).  a + b is commutative, so both copies
+// hold identical bits.  The y / z face passes and the class-list pass that follow never touch an i-face sector
+// for its own sake any more.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -110,7 +111,7 @@ template <int NE, int NW, int DS, int NF, int MAXREG, bool LIST = false, int XS 
 __global__ void __launch_bounds__(V3Cfg<NE, NW, DS, NF>::NTHREADS, 1) __maxnreg__(MAXREG)
 adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
   using C = V3Cfg<NE, NW, DS, NF>;
-  // XS = 2: lane (g,0) re-loads the previous element's i = 7 value from L2 (__ldcg) and rewrites it -- no cross-lane
+  // XS != 0: lane (g,0) re-loads the previous element's i = 7 value from L2 and rewrites it -- no cross-lane
   // traffic.  (Tried and dropped, r02c/r02j: the value kept in shared memory or in registers of lane (g,3) and
   // swapped with shfl.xor(3): 4-5 % slower.)
   static_assert(!XS || !LIST, "the x stage runs on contiguous element runs");
@@ -228,6 +229,10 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     [[maybe_unused]] unsigned long long xm = 0ull;
     if constexpr (XS) xm = __ldg(p.xmask + e);
 
+    // the s/t fragments of D are read from the table once per element (they feed 16 DMMA pairs each); the r
+    // fragments and the weights, used once per plane, are read where they are needed
+    const double dsf0 = CT(CT_DSF), dsf1 = CT(CT_DSF + 1), dsb0 = CT(CT_DSB), dsb1 = CT(CT_DSB + 1);
+
     // ---- t-derivatives of the base flow, per (component, j) slab -> Wt --------------------------------
 #pragma unroll
     for (int tk = 0; tk < NTASK / NW; tk++) {
@@ -236,8 +241,8 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       const double* __restrict__ Uc = p.ub[c] + ebase + 8 * j + g;
       const double b0 = __ldg(Uc + 64 * q), b1 = __ldg(Uc + 64 * (q + 4));
       double2 acc = make_double2(0.0, 0.0);
-      dmma(acc, CT(CT_DSF), b0);
-      dmma(acc, CT(CT_DSF + 1), b1);
+      dmma(acc, dsf0, b0);
+      dmma(acc, dsf1, b1);
       *reinterpret_cast<double2*>(Wt + c * N + wt_off(2 * q, j, g)) = acc;
     }
     named_bar_sync(bar_id, C::NSLOT_THR);
@@ -249,7 +254,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       const int k = wid + pi * NW;
       const int qoff = 64 * k + pl2;
       double2 ub2[3], gr[3], gs[3], gt[3];
-      const double drf0 = CT(CT_DRF), drf1 = CT(CT_DRF + 1), dsf0 = CT(CT_DSF), dsf1 = CT(CT_DSF + 1);
+      const double drf0 = CT(CT_DRF), drf1 = CT(CT_DRF + 1);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const double* __restrict__ Uc = p.ub[c] + ebase + 64 * k;
@@ -376,7 +381,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
         *reinterpret_cast<double2*>(scr + c * PLANE + scr_w) = Fs[c];
       }
       __syncwarp();
-      const double drb0 = CT(CT_DRB), drb1 = CT(CT_DRB + 1), dsb0 = CT(CT_DSB), dsb1 = CT(CT_DSB + 1);
+      const double drb0 = CT(CT_DRB), drb1 = CT(CT_DRB + 1);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         double2 acc = fpw[c];
@@ -391,11 +396,12 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
     }
     named_bar_sync(bar_id, C::NSLOT_THR);
 
-    [[maybe_unused]] double pv[NPL][3];
+    // ---- x stage, part 1: fetch the previous element's i = 7 values (L2 hits, ~1 us under load) as asynchronous
+    //      8-byte copies (LDGSTS) into the warp's scratch, which is free between the plane loop and the next
+    //      element's: no register is held across the transposed t contraction, whose work hides the latency.
+    //      (The same fetch into registers: 1-1.5 % slower step, r02v; right before the stores: +7 %, r02l.)
     [[maybe_unused]] bool xdo[NPL];
-    // x stage: fetch the previous element's i = 7 values (L2 hits, ~1 us under load) before the transposed t
-    // contraction, whose work hides the latency (fetching right before the stores: +7 % step time, r02l)
-    auto xs_fetch = [&]() {
+    if constexpr (XS != 0) {
 #pragma unroll
       for (int pi = 0; pi < NPL; pi++) {
         const int k = wid + pi * NW;
@@ -403,11 +409,11 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
         if (xdo[pi]) {
           const size_t xoff = ebase - N + 64 * k + 8 * g + 7;        // (i = 7, j = g, k) of the slot's previous element
 #pragma unroll
-          for (int c = 0; c < 3; c++) pv[pi][c] = __ldcg(p.f[c] + xoff);
+          for (int c = 0; c < 3; c++) cp_async_8(scr + (pi * 3 + c) * 8 + g, p.f[c] + xoff);
         }
       }
-    };
-    if constexpr (XS == 2) xs_fetch();
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     // ---- transposed t contraction per (component, j) slab, in place in Wt ------------------------------
 #pragma unroll
@@ -416,14 +422,22 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
       const int c = task >> 3, j = task & 7;
       const double b0 = Wt[c * N + wt_off(g, j, q)], b1 = Wt[c * N + wt_off(g, j, q + 4)];
       double2 acc = make_double2(0.0, 0.0);
-      dmma(acc, CT(CT_DSB), b0);
-      dmma(acc, CT(CT_DSB + 1), b1);
+      dmma(acc, dsb0, b0);
+      dmma(acc, dsb1, b1);
       __syncwarp();
       *reinterpret_cast<double2*>(Wt + c * N + wt_off(2 * q, j, g)) = acc;
     }
     named_bar_sync(bar_id, C::NSLOT_THR);
 
     // ---- final: f = (fpw + R_r + R_s) + R_t, 128-bit stores straight from the fragments -----------------
+    [[maybe_unused]] double pv[NPL][3];
+    if constexpr (XS != 0) {     // x stage, part 2: the lane that issued a copy reads it back (its own copies only)
+      asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+      for (int pi = 0; pi < NPL; pi++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) pv[pi][c] = xdo[pi] ? scr[(pi * 3 + c) * 8 + g] : 0.0;
+    }
 #pragma unroll
     for (int pi = 0; pi < NPL; pi++) {
       const int k = wid + pi * NW;
@@ -433,7 +447,7 @@ adjrhs_v3_kernel(const __grid_constant__ KParams2<8> p) {
         double2 o;
         o.x = cacc[pi][c].x + rt.x;
         o.y = cacc[pi][c].y + rt.y;
-        if constexpr (XS == 2) {
+        if constexpr (XS != 0) {
           if (xdo[pi]) { o.x += pv[pi][c]; p.f[c][ebase - N + 64 * k + 8 * g + 7] = o.x; }
         }
         *reinterpret_cast<double2*>(p.f[c] + ebase + 64 * k + pl2) = o;

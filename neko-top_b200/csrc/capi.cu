@@ -149,6 +149,7 @@ struct Handle {
   bool xs_valid = false;
   int xs_level = 0;                // level the lists below were built for
   int xs_nslots = 0;               // element slots of the grid the links were built for
+  int face_ctas = 8;               // CTAs of 256 threads per SM of the y / z face passes (B200_FACE_CTAS)
   int xs_nolink = 0;               // B200_XS_NOLINK=1 (diagnostic): same element map, no class staged
   unsigned long long* xs_mask[3] = {};   // per element: nodes of the i/j/k = 0 face summed with the neighbour's 7 face
   int* xs_pred[3] = {};            // neighbour element across that face
@@ -821,7 +822,7 @@ int build_xstage(Handle* h, int level) {
 int gs_face_passes(Handle* h, double* f0, double* f1, double* f2) {
   if (h->xs_level < 2) return B200_OK;
   const int threads = 256;
-  const int grid = grid_for((int64_t)h->nelv * 32, threads, h->num_sm, 8);
+  const int grid = grid_for((int64_t)h->nelv * 32, threads, h->num_sm, h->face_ctas);
   if (h->xs_have[1]) {
     gs_face_pass_kernel<1><<<grid, threads, 0, h->stream>>>(f0, f1, f2, h->xs_pred[1], h->xs_mask[1], h->nelv);
     LAUNCHED();
@@ -979,6 +980,8 @@ int b200_adjrhs_create(void** handle, const int* lx, const int* nelv, const int*
   if (g) h->gs_un = atoi(g);
   g = getenv("B200_XSTAGE");
   if (g) h->xs_enable = std::min(2, std::max(0, atoi(g)));
+  g = getenv("B200_FACE_CTAS");
+  if (g) h->face_ctas = std::min(8, std::max(1, atoi(g)));
   g = getenv("B200_XS_NOLINK");
   if (g) h->xs_nolink = atoi(g) != 0;
   *handle = h;

@@ -494,6 +494,57 @@ def test_step_xstage(oracle, kind):
     op.free()
 
 
+@pytest.mark.parametrize("lx,ne", [(4, (16, 10, 9)), (5, (14, 12, 10)), (6, (12, 10, 8)), (7, (10, 10, 8)),
+                                   (9, (10, 8, 6)), (10, (9, 8, 6))])
+def test_step_other_orders_irregular_mesh(oracle, lx, ne):
+    """b200_adjrhs_step at the other polynomial orders (the pencil kernels) on a mesh with more elements than
+    element slots, some unrelated nodes identified and the i = lx-1 face of the last element of every row glued to
+    i = 0 of the first: <= 1e-12 against the oracle, all copies of a node identical, static forcing, host-buffer
+    step bit-identical.  The staged summation is an lx = 8 feature (measured slower with the pencil kernels,
+    profiles/r02C_*): its setting is accepted, reports inactive, and changes no bit."""
+    P = Problem(lx, ne=ne, deform=0.02)
+    keys = P.keys.reshape(-1).numpy().copy()
+    k4 = keys.reshape(ne[2], ne[1], ne[0], lx, lx, lx)
+    k4[:, :, -1, :, :, -1] = k4[:, :, 0, :, :, 0]
+    keys = k4.reshape(-1).copy()
+    rng = np.random.default_rng(29 + lx)
+    sel = rng.random(keys.size) < 0.005
+    keys[sel] = keys.max() + 1 + rng.integers(0, sel.sum() // 3 + 1, sel.sum())
+    fo, so, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho)
+    cid, nc = oracle.gs_classes(keys)
+    ref = [oracle.gs_add(fo[c], cid, nc) for c in range(3)]
+    op, _ = _fused(P)
+    op.gs.init(keys)
+    gcid, gnc = op.gs.classes()
+    assert gnc == nc and np.array_equal(gcid, cid)
+    v, ub, rho = P.cuda("v"), P.cuda("ub"), P.cuda("rho")
+    res = {}
+    for level in (0, 2):
+        op.set_xstage(level)
+        f, sens = [_nan(P.n) for _ in range(3)], _nan(P.n)
+        for _ in range(2):
+            op.step(v, ub, f, rho=rho, sens=sens)
+        active, nstaged, nleft, ntot = op.xstage_info()
+        assert active == 0 and nstaged == 0 and nleft == ntot == nc
+        res[level] = (f, sens)
+        for c in range(3):
+            assert rel_l2(f[c].cpu().numpy(), ref[c]) <= TOL, (lx, level, c)
+            assert _copies_identical(f[c].cpu().numpy(), cid), (lx, level, c)
+        assert rel_l2(sens.cpu().numpy(), so) <= TOL
+    for c in range(3):
+        assert torch.equal(res[0][0][c], res[2][0][c])
+    assert torch.equal(res[0][1], res[2][1])
+    fs = [torch.as_tensor(np.random.default_rng(4).standard_normal(P.n)).cuda() for _ in range(3)]
+    fos, _, _ = oracle.adjoint_rhs(P.v, P.ub, lx, P.nelv, P.D, P.w, P.G, P.B, rho=P.rho,
+                                   fstatic=[a.cpu().numpy() for a in fs])
+    g3 = [_nan(P.n) for _ in range(3)]
+    op.step(v, ub, g3, rho=rho, fstatic=fs)
+    for c in range(3):
+        assert rel_l2(g3[c].cpu().numpy(), oracle.gs_add(fos[c], cid, nc)) <= TOL
+    _check_step_host(op, v, ub, rho, res[0][0], res[0][1])
+    op.free()
+
+
 def test_step_gs_packed_lists_irregular_classes(oracle):
     """Node classes of every size (3, 5..16 members and > 16, which stay with the list kernel): keys of a
     box mesh folded modulo a small number so that unrelated nodes are identified."""

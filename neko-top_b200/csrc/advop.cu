@@ -2,9 +2,11 @@
 #include "advop.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "advop_kernel.cuh"
+#include "advop_mma_kernel.cuh"
 #include "deriv_kernels.cuh"
 #include "helm_kernels.cuh"
 
@@ -54,6 +56,45 @@ cudaError_t launch_one(const AdvLaunch& a) {
   return cudaGetLastError();
 }
 
+// lx = 8 / lxd = 12 dealiased adjoint operator on the FP64 tensor cores (advop_mma_kernel.cuh); B200_ADVOP_MMA=0
+// selects the column-per-thread kernel instead (diagnostic)
+bool use_mma_kernel() {
+  static const int on = [] { const char* g = getenv("B200_ADVOP_MMA"); return g ? atoi(g) : 1; }();
+  return on != 0;
+}
+
+cudaError_t launch_mma(const AdvLaunch& a) {
+  using C = AdvMmaCfg;
+  static_assert(C::SMEM <= 227 * 1024, "tensor-core dealiased operator exceeds the shared memory of an SM");
+  AdvMmaParams p;
+  memset(&p, 0, sizeof p);
+  for (int i = 0; i < 96; i++) p.J[i] = a.J[i];
+  for (int l = 0; l < 8; l++)
+    for (int i = 0; i < 12; i++) {        // DJ(i,l) = sum_m D(i,m) J(m,l)
+      double s = 0.0;
+      for (int m = 0; m < 12; m++) s += a.D[i + 12 * m] * a.J[m + 12 * l];
+      p.DJ[i + 12 * l] = s;
+    }
+  for (int i = 0; i < 12; i++) p.wd[i] = a.wd[i];
+  for (int c = 0; c < 3; c++) { p.v[c] = a.v[c]; p.vb[c] = a.vb[c]; p.f[c] = a.f[c]; p.fs[c] = a.fs[c]; }
+  for (int g = 0; g < 9; g++) p.G[g] = a.G[g];
+  p.rho = a.rho; p.B = a.B; p.sens = a.sens; p.chi_out = a.chi_out;
+  p.elem_list = a.elem_list; p.nelem = a.nelem; p.elem_base = a.elem_base; p.flags = a.flags;
+  p.f_min = a.f_min; p.f_max = a.f_max; p.q = a.q; p.K_lube = a.K_lube; p.K_sens = a.K_sens;
+  static unsigned long long dev_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !(dev_done >> dev & 1ull)) {
+    if (dev < 64) dev_done |= 1ull << dev;
+    cudaError_t e = cudaFuncSetAttribute(advop_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = std::min(a.nelem, a.num_sm);
+  if (grid < 1) return cudaSuccess;
+  advop_mma_kernel<<<grid, C::NTHR, C::SMEM, a.stream>>>(p);
+  return cudaGetLastError();
+}
+
 template <int LX>
 cudaError_t launch_lx(const AdvLaunch& a, const char** msg) {
   constexpr int LXD = 3 * LX / 2;
@@ -66,7 +107,10 @@ cudaError_t launch_lx(const AdvLaunch& a, const char** msg) {
     *msg = "dealiased operator: only lxd = 3*lx/2 (the factory default, advection_adjoint_fctry.f90:70) is instantiated";
     return cudaErrorInvalidValue;
   }
-  if (a.mode == ADV_ADJOINT) return launch_one<LX, LXD, ADV_ADJOINT>(a);
+  if (a.mode == ADV_ADJOINT) {
+    if constexpr (LX == 8) if (use_mma_kernel()) return launch_mma(a);
+    return launch_one<LX, LXD, ADV_ADJOINT>(a);
+  }
   return launch_one<LX, LXD, ADV_LINEAR>(a);
 }
 

@@ -5,8 +5,9 @@
 // Why: the column-per-thread kernel is latency-bound at 2.5 warps per scheduler (168 registers x 160 threads, 104 KB
 // per element; ncu r02h: issue 25 %, fp64 pipe 26 %, 45 % of the shared-memory wavefront peak) because every DFMA of
 // an r/s contraction needs its own shared-memory operand.  A DMMA takes one 64-bit fragment load per 256 FMAs, needs
-// ~60 registers per warp instead of 168, and so 16 warps share one SM with the whole element (15 fine-grid arrays)
-// in shared memory.
+// ~60 registers per warp instead of 168, and so 18 warps share one SM with the whole element (15 fine-grid arrays)
+// in shared memory.  Measured (profiles/r02D): fused dealiased step 6.56 -> 3.08 ms at 32^3 elements (2.56 -> 5.45
+// GDOF/s), un-fused drop-in 5.80 -> 3.02 ms.
 //
 // Formulation.  With J (12x8) the GLL -> Gauss-Legendre interpolation, D (12x12) the fine-grid derivative and
 // DJ = D J (12x8, formed on the host), per element:
@@ -30,7 +31,15 @@
 // C = (batch g; output 2q, 2q+1) -- chosen per stage so that the two C values are adjacent in memory (128-bit stores).
 //
 // Shared memory: 15 arrays [k][j][i] with row stride 12 and plane stride 148 doubles (148 = 4 mod 16: the four
-// contraction indices of a t-stage fragment load fall into different banks), 216.8 KB; one CTA of 512 threads per SM.
+// contraction indices of a t-stage fragment load fall into different banks), 220 KB with the fragment tables; one CTA
+// of 18 warps per SM (96 registers).  Stages per element, separated by CTA barriers:
+//   load | F1 | F2 | F3 -> point-wise -> T1 (one 8-column tile per warp: these three only couple the 12 planes of a
+//   column, so there is no CTA barrier inside) | T2 | T3 | epilogue (one GLL point per thread).
+// The matrix fragments sit in registers for a whole stage (re-loading them per tile was 45 % of the load wavefronts);
+// the epilogue's inputs and the next element's fields are loaded two stages early with volatile loads; the fine-grid
+// geometry of the element is prefetched into L2 when the element starts.  ncu (r02D5): DMMA pipe 45 % busy, shared-
+// memory wavefronts 43 %; the rest is the point-wise phase (21 %, LSU-bound: 27 shared + 9 global accesses per point)
+// and barrier waits (18 %: 18 tiles over 4 schedulers, 48 / 24 tasks over 18 warps in F1 / T3).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -64,11 +73,12 @@ struct AdvMmaCfg {
   static constexpr int PS = 148;                  // plane stride in shared memory
   static constexpr int AS = LXD * PS;             // array stride
   static constexpr int NARR = 15;                 // TV 0..2, TB 3..5, DR 6..8, DS 9..11, DT 12..14
-  static constexpr int NFRAG = 14;                // J: 0..3 (mt*2+ks), DJ: 4..7, J^T: 8..10 (ks), DJ^T: 11..13
+  static constexpr int NFRAG = 28;                // J: 0..3 (mt*2+ks), DJ: 4..7, J^T: 8..10 (ks), DJ^T: 11..13 with output row
+                                                  // pi(g) (matrix as A); 14..27: the same with output row g (matrix as B)
   static constexpr int FT_OFF = NARR * AS;
   static constexpr int W_OFF = FT_OFF + NFRAG * 32;
-  static constexpr int SMEM = (W_OFF + 12) * 8;
-  static constexpr int NTHR = 512, NWARP = 16;
+  static constexpr int SMEM = (W_OFF + 12) * 8;          // 220.4 KB
+  static constexpr int NTHR = 576, NWARP = 18;     // 18 warps = the 18 column tiles of the fused F3 / point-wise / T1 stage
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -77,6 +87,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 __device__ __forceinline__ void st2(double* p, double a, double b) {
   *reinterpret_cast<double2*>(p) = make_double2(a, b);
+}
+// a load the compiler must leave where it is written (issued two stages before its use)
+__device__ __forceinline__ double ldg_pinned(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_pinned_rw(const double* p) {      // for data this kernel also writes (f, in/out)
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ void adv_l2_prefetch(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -92,16 +113,22 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int pg = (g & 4) | ((g & 1) << 1) | ((g >> 1) & 1);     // pi(g)
   const unsigned flags = p.flags;
 
-  // matrix fragments [fragment][lane] and weights
+  // matrix fragments [fragment][lane] and weights.  Fragments 0..13 carry output row pi(g), pi = (0 2 1 3 4 6 5 7):
+  // the two g of a quarter warp then store rows two apart (24 or 296 words = 4 mod 8 sixteen-byte banks) and the
+  // 128-bit stores of a C fragment are conflict-free; with consecutive rows (12 / 148 words = 6 / 2 mod 8) every one
+  // of them was a 2-way conflict (ncu r02D: 43 % of the store wavefronts).
   for (int idx = tid; idx < C::NFRAG * 32; idx += C::NTHR) {
-    const int fid = idx >> 5, gg = (idx & 31) >> 2, qq = idx & 3;
+    const int fr = idx >> 5, gg0 = (idx & 31) >> 2, qq = idx & 3;
+    const int fid = fr % 14;
+    const int gg = (fr < 14) ? ((gg0 & 4) | ((gg0 & 1) << 1) | ((gg0 >> 1) & 1)) : gg0;
     double val;
-    if (fid < 8) {                     // forward: M(output a = 8 mt + g, contraction l = 4 ks + q), rows >= 12 are zero
+    if (fid < 8) {                     // forward: M(output a = 8 mt + row, contraction l = 4 ks + q), rows >= 12 are zero
       const int mt = (fid & 3) >> 1, ks = fid & 1, o = 8 * mt + gg, c = 4 * ks + qq;
       val = (o < 12) ? (fid < 4 ? p.J[o + 12 * c] : p.DJ[o + 12 * c]) : 0.0;
-    } else {                           // backward: M(output l = g, contraction a = 4 ks + q) = J(a, l)
+    } else {                           // backward: M(output l = row, contraction a = 4 ks + q) = J(a, l)
       const int ks = (fid - 8) % 3, c = 4 * ks + qq;
       val = (fid < 11) ? p.J[c + 12 * gg] : p.DJ[c + 12 * gg];
     }
@@ -114,8 +141,9 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
   const int goff = gl + 12 * gm + PS * gn;
 
   auto elem_of = [&](int it) { return p.elem_list ? __ldg(p.elem_list + it) : p.elem_base + it; };
-  double un[6];
-  if ((int)blockIdx.x < p.nelem) {
+  const bool gth = tid < N;          // threads that own a GLL point
+  double un[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if ((int)blockIdx.x < p.nelem && gth) {
     const size_t eb = (size_t)elem_of(blockIdx.x) * N + tid;
 #pragma unroll
     for (int c = 0; c < 3; c++) { un[c] = __ldg(p.v[c] + eb); un[3 + c] = __ldg(p.vb[c] + eb); }
@@ -125,244 +153,307 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
   for (int it = blockIdx.x; it < p.nelem; it += gridDim.x) {
     const int e = elem_of(it);
     const size_t eb = (size_t)e * N, ebd = (size_t)e * ND;
+    double ep_bm = 0.0, ep_rho = 0.0, ep_f[3] = {0.0, 0.0, 0.0};
+    if (gth) {
 #pragma unroll
-    for (int f = 0; f < 6; f++) sm[f * AS + goff] = un[f];
+      for (int f = 0; f < 6; f++) sm[f * AS + goff] = un[f];
+    }
     if (tid < 9) adv_l2_prefetch(p.G[tid] + ebd, ND * 8);
     __syncthreads();
 
-    // ---- F1: r axis.  batch (m, n): tile t = n, entry g = m; output a = 2q, 2q+1 (+8 nt): matrix as B ------------
-    for (int tk = warp; tk < 48; tk += C::NWARP) {
-      const int fo = tk >> 3, t = tk & 7;
-      const bool isb = fo < 3;                       // base-flow fields first (twice the work)
-      double* arr = sm + (isb ? 3 + fo : fo - 3) * AS + 12 * g + PS * t;
-      const double d0 = arr[q], d1 = arr[4 + q];
+    // ---- F1: r axis.  batch (m, n): tile t = n, entry g = row m = pi(g); output a = 2q, 2q+1 (+8 nt): matrix as B ---
+    {
+      double mj[4], md[4];
 #pragma unroll
-      for (int nt = 0; nt < 2; nt++) {
-        double c0 = 0.0, c1 = 0.0;
-        dmma884(c0, c1, d0, FT[(nt * 2 + 0) * 32 + lane]);
-        dmma884(c0, c1, d1, FT[(nt * 2 + 1) * 32 + lane]);
-        if (nt == 0 || q < 2) st2(arr + 8 * nt + 2 * q, c0, c1);
-      }
-      if (isb) {
-        double* dr = sm + (6 + fo) * AS + 12 * g + PS * t;
+      for (int x = 0; x < 4; x++) { mj[x] = FT[(14 + x) * 32 + lane]; md[x] = FT[(18 + x) * 32 + lane]; }
+      for (int tk = warp; tk < 48; tk += C::NWARP) {
+        const int fo = tk >> 3, t = tk & 7;
+        const bool isb = fo < 3;                       // base-flow fields first (twice the work)
+        double* arr = sm + (isb ? 3 + fo : fo - 3) * AS + 12 * pg + PS * t;
+        const double d0 = arr[q], d1 = arr[4 + q];
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           double c0 = 0.0, c1 = 0.0;
-          dmma884(c0, c1, d0, FT[(4 + nt * 2 + 0) * 32 + lane]);
-          dmma884(c0, c1, d1, FT[(4 + nt * 2 + 1) * 32 + lane]);
-          if (nt == 0 || q < 2) st2(dr + 8 * nt + 2 * q, c0, c1);
+          dmma884(c0, c1, d0, mj[nt * 2 + 0]);
+          dmma884(c0, c1, d1, mj[nt * 2 + 1]);
+          if (nt == 0 || q < 2) st2(arr + 8 * nt + 2 * q, c0, c1);
         }
-      }
-    }
-    __syncthreads();
-
-    // ---- F2: s axis.  batch beta = a + 12 n (96); output b = g (+8 mt): matrix as A ----------------------------------
-    for (int tk = warp; tk < 72; tk += C::NWARP) {
-      const int fo = tk / 12, t = tk - 12 * fo;
-      const bool isb = fo < 3;
-      const int bl = 8 * t + g, bs = 8 * t + 2 * q;                 // load / store batch entry
-      const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;           // + 48 per k-step
-      const int so = (bs % 12) + PS * (bs / 12) + 12 * g;           // + 96 for mt = 1
-      double* arr = sm + (isb ? 3 + fo : fo - 3) * AS;
-      const double d0 = arr[lo], d1 = arr[lo + 48];
-      double e0 = 0.0, e1 = 0.0;
-      double* dr = sm + (6 + fo) * AS;
-      double* ds = sm + (9 + fo) * AS;
-      if (isb) { e0 = dr[lo]; e1 = dr[lo + 48]; }
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-        const double j0 = FT[(mt * 2 + 0) * 32 + lane], j1 = FT[(mt * 2 + 1) * 32 + lane];
-        double c0 = 0.0, c1 = 0.0;
-        dmma884(c0, c1, j0, d0);
-        dmma884(c0, c1, j1, d1);
-        if (mt == 0 || g < 4) st2(arr + so + 96 * mt, c0, c1);
         if (isb) {
-          double b0 = 0.0, b1 = 0.0, a0 = 0.0, a1 = 0.0;
-          dmma884(b0, b1, FT[(4 + mt * 2 + 0) * 32 + lane], d0);
-          dmma884(b0, b1, FT[(4 + mt * 2 + 1) * 32 + lane], d1);
-          dmma884(a0, a1, j0, e0);
-          dmma884(a0, a1, j1, e1);
-          if (mt == 0 || g < 4) { st2(ds + so + 96 * mt, b0, b1); st2(dr + so + 96 * mt, a0, a1); }
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- F3: t axis.  batch beta = a + 12 b (144, contiguous); output c = g (+8 mt): matrix as A ------------------
-    for (int tk = warp; tk < 108; tk += C::NWARP) {
-      const int fo = tk / 18, t = tk - 18 * fo;
-      const bool isb = fo < 3;
-      const int lo = 8 * t + g + PS * q;                            // + 4 PS per k-step
-      const int so = 8 * t + 2 * q + PS * g;                        // + 8 PS for mt = 1
-      double* arr = sm + (isb ? 3 + fo : fo - 3) * AS;
-      double* dr = sm + (6 + fo) * AS;
-      double* ds = sm + (9 + fo) * AS;
-      double* dt = sm + (12 + fo) * AS;
-      const double d0 = arr[lo], d1 = arr[lo + 4 * PS];
-      double r0 = 0.0, r1 = 0.0, s0 = 0.0, s1 = 0.0;
-      if (isb) { r0 = dr[lo]; r1 = dr[lo + 4 * PS]; s0 = ds[lo]; s1 = ds[lo + 4 * PS]; }
+          double* dr = sm + (6 + fo) * AS + 12 * pg + PS * t;
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-        const double j0 = FT[(mt * 2 + 0) * 32 + lane], j1 = FT[(mt * 2 + 1) * 32 + lane];
-        const bool on = (mt == 0 || g < 4);
-        double c0 = 0.0, c1 = 0.0;
-        dmma884(c0, c1, j0, d0);
-        dmma884(c0, c1, j1, d1);
-        if (on) st2(arr + so + 8 * PS * mt, c0, c1);
-        if (isb) {
-          double t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-          dmma884(t0, t1, FT[(4 + mt * 2 + 0) * 32 + lane], d0);
-          dmma884(t0, t1, FT[(4 + mt * 2 + 1) * 32 + lane], d1);
-          dmma884(a0, a1, j0, s0);
-          dmma884(a0, a1, j1, s1);
-          dmma884(b0, b1, j0, r0);
-          dmma884(b0, b1, j1, r1);
-          if (on) {
-            st2(dt + so + 8 * PS * mt, t0, t1);
-            st2(ds + so + 8 * PS * mt, a0, a1);
-            st2(dr + so + 8 * PS * mt, b0, b1);
+          for (int nt = 0; nt < 2; nt++) {
+            double c0 = 0.0, c1 = 0.0;
+            dmma884(c0, c1, d0, md[nt * 2 + 0]);
+            dmma884(c0, c1, d1, md[nt * 2 + 1]);
+            if (nt == 0 || q < 2) st2(dr + 8 * nt + 2 * q, c0, c1);
           }
         }
       }
     }
     __syncthreads();
 
-    // ---- point-wise stage on the fine grid (in place: R -> TV, Fr -> DR, Fs -> DS, Ft -> DT) -------------------------
-#pragma unroll 2
-    for (int pt = tid; pt < ND; pt += C::NTHR) {
-      const int c = pt / PL, ab = pt - PL * c, b = ab / 12, a = ab - 12 * b;
-      double* P = sm + ab + PS * c;
-      double gg[9];
+    {
+      double mj[4], md[4];     // J, DJ as A operand with output row pi(g): [mt*2 + ks]
 #pragma unroll
-      for (int x = 0; x < 9; x++) gg[x] = __ldg(p.G[x] + ebd + pt);
-      const double w3 = W[a] * W[b] * W[c];
-      double tv[3], tb[3];
+      for (int x = 0; x < 4; x++) { mj[x] = FT[x * 32 + lane]; md[x] = FT[(4 + x) * 32 + lane]; }
+
+      // ---- F2: s axis.  batch beta = a + 12 n (96); output b = pi(g) (+8 mt): matrix as A ---------------------------
+      for (int tk = warp; tk < 72; tk += C::NWARP) {
+        const int fo = tk / 12, t = tk - 12 * fo;
+        const bool isb = fo < 3;
+        const int bl = 8 * t + g, bs = 8 * t + 2 * q;                 // load / store batch entry
+        const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;           // + 48 per k-step
+        const int so = (bs % 12) + PS * (bs / 12) + 12 * pg;          // + 96 for mt = 1
+        double* arr = sm + (isb ? 3 + fo : fo - 3) * AS;
+        const double d0 = arr[lo], d1 = arr[lo + 48];
+        double e0 = 0.0, e1 = 0.0;
+        double* dr = sm + (6 + fo) * AS;
+        double* ds = sm + (9 + fo) * AS;
+        if (isb) { e0 = dr[lo]; e1 = dr[lo + 48]; }
 #pragma unroll
-      for (int x = 0; x < 3; x++) { tv[x] = P[x * AS]; tb[x] = P[(3 + x) * AS]; }
-      double R0 = 0.0, R1 = 0.0, R2 = 0.0;
-#pragma unroll
-      for (int x = 0; x < 3; x++) {
-        const double dr = P[(6 + x) * AS], ds = P[(9 + x) * AS], dt = P[(12 + x) * AS];
-        const double dx = w3 * (gg[0] * dr + gg[1] * ds + gg[2] * dt);
-        const double dy = w3 * (gg[3] * dr + gg[4] * ds + gg[5] * dt);
-        const double dz = w3 * (gg[6] * dr + gg[7] * ds + gg[8] * dt);
-        R0 = fma(tv[x], dx, R0);
-        R1 = fma(tv[x], dy, R1);
-        R2 = fma(tv[x], dz, R2);
+        for (int mt = 0; mt < 2; mt++) {
+          double c0 = 0.0, c1 = 0.0;
+          dmma884(c0, c1, mj[mt * 2], d0);
+          dmma884(c0, c1, mj[mt * 2 + 1], d1);
+          if (mt == 0 || g < 4) st2(arr + so + 96 * mt, c0, c1);
+          if (isb) {
+            double b0 = 0.0, b1 = 0.0, a0 = 0.0, a1 = 0.0;
+            dmma884(b0, b1, md[mt * 2], d0);
+            dmma884(b0, b1, md[mt * 2 + 1], d1);
+            dmma884(a0, a1, mj[mt * 2], e0);
+            dmma884(a0, a1, mj[mt * 2 + 1], e1);
+            if (mt == 0 || g < 4) { st2(ds + so + 96 * mt, b0, b1); st2(dr + so + 96 * mt, a0, a1); }
+          }
+        }
       }
-      const double cr = w3 * (tb[0] * gg[0] + tb[1] * gg[3] + tb[2] * gg[6]);
-      const double cs = w3 * (tb[0] * gg[1] + tb[1] * gg[4] + tb[2] * gg[7]);
-      const double ct = w3 * (tb[0] * gg[2] + tb[1] * gg[5] + tb[2] * gg[8]);
-      P[0 * AS] = R0; P[1 * AS] = R1; P[2 * AS] = R2;
+      __syncthreads();
+
+      // ---- F3 -> point-wise -> T1 on one tile of 8 (i,j) columns per warp, no CTA barrier in between: the t-axis stages
+      // and the point-wise work only couple the 12 planes of a column, so a warp carries its 96 points through all
+      // three, and the warps drift apart -- tensor-core, FP64 and load phases of different warps overlap.
+      // F3: t axis.  batch beta = a + 12 b (contiguous); output c = pi(g) (+8 mt): matrix as A
+      const int t = warp;
+      {
+        const int lo = 8 * t + g + PS * q;                            // + 4 PS per k-step
+        const int so = 8 * t + 2 * q + PS * pg;                       // + 8 PS for mt = 1
+#pragma unroll 1
+        for (int fo = 0; fo < 3; fo++) {                              // base flow: T, d_t, d_s, d_r
+          double* arr = sm + (3 + fo) * AS;
+          double* dr = sm + (6 + fo) * AS;
+          double* ds = sm + (9 + fo) * AS;
+          double* dt = sm + (12 + fo) * AS;
+          const double d0 = arr[lo], d1 = arr[lo + 4 * PS];
+          const double r0 = dr[lo], r1 = dr[lo + 4 * PS], s0 = ds[lo], s1 = ds[lo + 4 * PS];
 #pragma unroll
-      for (int x = 0; x < 3; x++) {
-        P[(6 + x) * AS] = tv[x] * cr;
-        P[(9 + x) * AS] = tv[x] * cs;
-        P[(12 + x) * AS] = tv[x] * ct;
+          for (int mt = 0; mt < 2; mt++) {
+            double c0 = 0.0, c1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            dmma884(c0, c1, mj[mt * 2], d0);
+            dmma884(t0, t1, md[mt * 2], d0);
+            dmma884(a0, a1, mj[mt * 2], s0);
+            dmma884(b0, b1, mj[mt * 2], r0);
+            dmma884(c0, c1, mj[mt * 2 + 1], d1);
+            dmma884(t0, t1, md[mt * 2 + 1], d1);
+            dmma884(a0, a1, mj[mt * 2 + 1], s1);
+            dmma884(b0, b1, mj[mt * 2 + 1], r1);
+            if (mt == 0 || g < 4) {
+              st2(arr + so + 8 * PS * mt, c0, c1);
+              st2(dt + so + 8 * PS * mt, t0, t1);
+              st2(ds + so + 8 * PS * mt, a0, a1);
+              st2(dr + so + 8 * PS * mt, b0, b1);
+            }
+          }
+        }
+        {                                                             // adjoint velocity: T only
+          double d0[3], d1[3];
+#pragma unroll
+          for (int fo = 0; fo < 3; fo++) { d0[fo] = sm[fo * AS + lo]; d1[fo] = sm[fo * AS + lo + 4 * PS]; }
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+            double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int fo = 0; fo < 3; fo++) dmma884(c0[fo], c1[fo], mj[mt * 2], d0[fo]);
+#pragma unroll
+            for (int fo = 0; fo < 3; fo++) dmma884(c0[fo], c1[fo], mj[mt * 2 + 1], d1[fo]);
+            if (mt == 0 || g < 4) {
+#pragma unroll
+              for (int fo = 0; fo < 3; fo++) st2(sm + fo * AS + so + 8 * PS * mt, c0[fo], c1[fo]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+
+      // point-wise stage on the tile (in place: R -> TV, Fr -> DR, Fs -> DS, Ft -> DT).  lane -> column lane % 8, planes
+      // 4 r + (0, 2, 1, 3)[lane / 8]: the two planes of a half warp are 2 apart (296 words = 8 mod 16 banks).
+      // Tried and dropped: (a) handing R, Fr, Fs, Ft to T1 in registers (lane (g, q) taking the points of T1's data
+      // fragments) saves 24 shared-memory accesses per point but interleaves DFMA and DMMA in every warp; the two share
+      // the FP64 pipe and alternate badly (profiles/r01c: 27 instead of 58 FMA/clk/SM): 3.48 instead of 3.06 ms -- the
+      // phases stay apart; (b) two adjacent columns per lane with 128-bit accesses (half the LSU instructions, but two
+      // rounds with a third of the lanes idle in the second, and spills at the 96 registers of 18 warps): 3.69 ms.
+      {
+        const int col = 8 * t + (lane & 7), lg = lane >> 3;
+        const int pl0 = ((lg & 1) << 1) | (lg >> 1);
+        const int pb = col / 12, pa = col - 12 * pb;
+        const double wab = W[pa] * W[pb];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          const int c = 4 * r + pl0;
+          double* P = sm + col + PS * c;
+          double gg[9];
+#pragma unroll
+          for (int x = 0; x < 9; x++) gg[x] = __ldg(p.G[x] + ebd + col + PL * c);
+          const double w3 = wab * W[c];
+          double tv[3], tb[3];
+#pragma unroll
+          for (int x = 0; x < 3; x++) { tv[x] = w3 * P[x * AS]; tb[x] = P[(3 + x) * AS]; }
+          double R0 = 0.0, R1 = 0.0, R2 = 0.0;
+#pragma unroll
+          for (int x = 0; x < 3; x++) {
+            const double dr = P[(6 + x) * AS], ds = P[(9 + x) * AS], dt = P[(12 + x) * AS];
+            const double dx = gg[0] * dr + gg[1] * ds + gg[2] * dt;
+            const double dy = gg[3] * dr + gg[4] * ds + gg[5] * dt;
+            const double dz = gg[6] * dr + gg[7] * ds + gg[8] * dt;
+            R0 = fma(tv[x], dx, R0);
+            R1 = fma(tv[x], dy, R1);
+            R2 = fma(tv[x], dz, R2);
+          }
+          const double cr = tb[0] * gg[0] + tb[1] * gg[3] + tb[2] * gg[6];
+          const double cs = tb[0] * gg[1] + tb[1] * gg[4] + tb[2] * gg[7];
+          const double ct = tb[0] * gg[2] + tb[1] * gg[5] + tb[2] * gg[8];
+          P[0 * AS] = R0; P[1 * AS] = R1; P[2 * AS] = R2;
+#pragma unroll
+          for (int x = 0; x < 3; x++) {
+            P[(6 + x) * AS] = tv[x] * cr;
+            P[(9 + x) * AS] = tv[x] * cs;
+            P[(12 + x) * AS] = tv[x] * ct;
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    double pv0, pv1, pv2, b0, b1, b2;    // this element's GLL values for the epilogue
+    {
+      double jt[3], djt[3];    // J^T, DJ^T as A operand with output row pi(g)
+#pragma unroll
+      for (int ks = 0; ks < 3; ks++) { jt[ks] = FT[(8 + ks) * 32 + lane]; djt[ks] = FT[(11 + ks) * 32 + lane]; }
+
+      // ---- T1 on the warp's column tile: t axis, K = 12; output n = pi(g): matrix as A.  X1 -> R, X2 -> Fr, X3 -> Fs
+      {
+        const int t = warp;
+        const int lo = 8 * t + g + PS * q;
+        const int so = 8 * t + 2 * q + PS * pg;
+#pragma unroll 1
+        for (int c = 0; c < 3; c++) {
+          double* R = sm + c * AS;
+          double* Fr = sm + (6 + c) * AS;
+          double* Fs = sm + (9 + c) * AS;
+          const double* Ft = sm + (12 + c) * AS;
+          double x[3], y[3], u[3], w[3];
+#pragma unroll
+          for (int ks = 0; ks < 3; ks++) {
+            x[ks] = R[lo + 4 * PS * ks]; y[ks] = Ft[lo + 4 * PS * ks];
+            u[ks] = Fr[lo + 4 * PS * ks]; w[ks] = Fs[lo + 4 * PS * ks];
+          }
+          double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, h0 = 0.0, h1 = 0.0, k0 = 0.0, k1 = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < 3; ks++) {
+            dmma884(c0, c1, jt[ks], x[ks]);
+            dmma884(e0, e1, djt[ks], y[ks]);
+            dmma884(h0, h1, jt[ks], u[ks]);
+            dmma884(k0, k1, jt[ks], w[ks]);
+          }
+          st2(R + so, c0 + e0, c1 + e1);
+          st2(Fr + so, h0, h1);
+          st2(Fs + so, k0, k1);
+        }
+      }
+      __syncthreads();
+      // epilogue inputs and the next element's fields travel during T2 / T3 (pinned: the compiler would sink them)
+      pv0 = un[0]; pv1 = un[1]; pv2 = un[2]; b0 = un[3]; b1 = un[4]; b2 = un[5];
+      if (gth) {
+        if (flags & FLAG_ACCUM) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) ep_f[c] = ld_pinned_rw(p.f[c] + eb + tid);
+        } else {
+          if (flags & (FLAG_SOURCES | FLAG_FSTATIC)) ep_bm = ldg_pinned(p.B + eb + tid);
+          if (flags & FLAG_SOURCES) ep_rho = ldg_pinned(p.rho + eb + tid);
+        }
+        if (it + (int)gridDim.x < p.nelem) {
+          const size_t nb = (size_t)elem_of(it + gridDim.x) * N + tid;
+#pragma unroll
+          for (int c = 0; c < 3; c++) { un[c] = ldg_pinned(p.v[c] + nb); un[3 + c] = ldg_pinned(p.vb[c] + nb); }
+        }
+      }
+
+      // ---- T2: s axis, K = 12.  batch beta = i + 12 n (96); output m = pi(g).  part 0: Y1 -> R, part 1: Y2 -> Fr -----
+      for (int tk = warp; tk < 72; tk += C::NWARP) {
+        const int c = tk / 24, r = tk - 24 * c, t = r >> 1, part = r & 1;
+        const int bl = 8 * t + g, bs = 8 * t + 2 * q;
+        const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;            // + 48 per k-step
+        const int so = (bs % 12) + PS * (bs / 12) + 12 * pg;
+        double c0 = 0.0, c1 = 0.0;
+        if (part == 0) {
+          double* R = sm + c * AS;
+          const double* X3 = sm + (9 + c) * AS;
+          double x[3], y[3];
+#pragma unroll
+          for (int ks = 0; ks < 3; ks++) { x[ks] = R[lo + 48 * ks]; y[ks] = X3[lo + 48 * ks]; }
+          double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < 3; ks++) {
+            dmma884(c0, c1, jt[ks], x[ks]);
+            dmma884(e0, e1, djt[ks], y[ks]);
+          }
+          st2(R + so, c0 + e0, c1 + e1);
+        } else {
+          double* X2 = sm + (6 + c) * AS;
+          double x[3];
+#pragma unroll
+          for (int ks = 0; ks < 3; ks++) x[ks] = X2[lo + 48 * ks];
+#pragma unroll
+          for (int ks = 0; ks < 3; ks++) dmma884(c0, c1, jt[ks], x[ks]);
+          st2(X2 + so, c0, c1);
+        }
       }
     }
     __syncthreads();
 
-    // ---- T1: t axis, K = 12.  batch beta = i + 12 j; output n = g: matrix as A.  part 0: X1 -> R, part 1: X2, X3 -----
-    for (int tk = warp; tk < 108; tk += C::NWARP) {
-      const int c = tk / 36, r = tk - 36 * c, t = r >> 1, part = r & 1;
-      const int lo = 8 * t + g + PS * q;
-      const int so = 8 * t + 2 * q + PS * g;
-      double* a0 = sm + (part ? 6 + c : c) * AS;           // Fr | R
-      double* a1 = sm + (part ? 9 + c : 12 + c) * AS;      // Fs | Ft
-      double x[3], y[3];
+    // ---- T3: r axis, K = 12.  batch (m, n): tile t = n, entry g = row m = pi(g); output l = 2q, 2q+1: matrix as B ------
+    if (warp < 12) {
+      double jt[3], djt[3];
 #pragma unroll
-      for (int ks = 0; ks < 3; ks++) { x[ks] = a0[lo + 4 * PS * ks]; y[ks] = a1[lo + 4 * PS * ks]; }
-      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-      if (part == 0) {
-#pragma unroll
-        for (int ks = 0; ks < 3; ks++) {
-          dmma884(c0, c1, FT[(8 + ks) * 32 + lane], x[ks]);
-          dmma884(c0, c1, FT[(11 + ks) * 32 + lane], y[ks]);
-        }
-        st2(a0 + so, c0, c1);
-      } else {
-#pragma unroll
-        for (int ks = 0; ks < 3; ks++) {
-          const double jt = FT[(8 + ks) * 32 + lane];
-          dmma884(c0, c1, jt, x[ks]);
-          dmma884(e0, e1, jt, y[ks]);
-        }
-        st2(a0 + so, c0, c1);
-        st2(a1 + so, e0, e1);
-      }
-    }
-    __syncthreads();
-
-    // ---- T2: s axis, K = 12.  batch beta = i + 12 n (96); output m = g.  part 0: Y1 -> R, part 1: Y2 -> Fr -------------
-    for (int tk = warp; tk < 72; tk += C::NWARP) {
-      const int c = tk / 24, r = tk - 24 * c, t = r >> 1, part = r & 1;
-      const int bl = 8 * t + g, bs = 8 * t + 2 * q;
-      const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;            // + 48 per k-step
-      const int so = (bs % 12) + PS * (bs / 12) + 12 * g;
-      double c0 = 0.0, c1 = 0.0;
-      if (part == 0) {
-        double* R = sm + c * AS;
-        const double* X3 = sm + (9 + c) * AS;
+      for (int ks = 0; ks < 3; ks++) { jt[ks] = FT[(22 + ks) * 32 + lane]; djt[ks] = FT[(25 + ks) * 32 + lane]; }
+      for (int tk = warp; tk < 24; tk += 12) {
+        const int c = tk >> 3, t = tk & 7;
+        double* R = sm + c * AS + 12 * pg + PS * t;
+        const double* Y2 = sm + (6 + c) * AS + 12 * pg + PS * t;
         double x[3], y[3];
 #pragma unroll
-        for (int ks = 0; ks < 3; ks++) { x[ks] = R[lo + 48 * ks]; y[ks] = X3[lo + 48 * ks]; }
+        for (int ks = 0; ks < 3; ks++) { x[ks] = R[4 * ks + q]; y[ks] = Y2[4 * ks + q]; }
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 3; ks++) {
-          dmma884(c0, c1, FT[(8 + ks) * 32 + lane], x[ks]);
-          dmma884(c0, c1, FT[(11 + ks) * 32 + lane], y[ks]);
+          dmma884(c0, c1, x[ks], jt[ks]);
+          dmma884(e0, e1, y[ks], djt[ks]);
         }
-        st2(R + so, c0, c1);
-      } else {
-        double* X2 = sm + (6 + c) * AS;
-        double x[3];
-#pragma unroll
-        for (int ks = 0; ks < 3; ks++) x[ks] = X2[lo + 48 * ks];
-#pragma unroll
-        for (int ks = 0; ks < 3; ks++) dmma884(c0, c1, FT[(8 + ks) * 32 + lane], x[ks]);
-        st2(X2 + so, c0, c1);
+        st2(R + 2 * q, c0 + e0, c1 + e1);
       }
-    }
-    __syncthreads();
-
-    // ---- T3: r axis, K = 12.  batch (m, n): tile t = n, entry g = m; output l = 2q, 2q+1: matrix as B -------------------
-    for (int tk = warp; tk < 24; tk += C::NWARP) {
-      const int c = tk >> 3, t = tk & 7;
-      double* R = sm + c * AS + 12 * g + PS * t;
-      const double* Y2 = sm + (6 + c) * AS + 12 * g + PS * t;
-      double x[3], y[3];
-#pragma unroll
-      for (int ks = 0; ks < 3; ks++) { x[ks] = R[4 * ks + q]; y[ks] = Y2[4 * ks + q]; }
-      double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-      for (int ks = 0; ks < 3; ks++) {
-        dmma884(c0, c1, x[ks], FT[(8 + ks) * 32 + lane]);
-        dmma884(c0, c1, y[ks], FT[(11 + ks) * 32 + lane]);
-      }
-      st2(R + 2 * q, c0, c1);
-    }
-    // the next element's fields travel while this one is finished
-    if (it + (int)gridDim.x < p.nelem) {
-      const size_t nb = (size_t)elem_of(it + gridDim.x) * N + tid;
-#pragma unroll
-      for (int c = 0; c < 3; c++) { un[c] = __ldg(p.v[c] + nb); un[3 + c] = __ldg(p.vb[c] + nb); }
     }
     __syncthreads();
 
     // ---- epilogue at the GLL point of this thread ------------------------------------------------------------------------
-    {
+    if (gth) {
       const double o0 = sm[0 * AS + goff], o1 = sm[1 * AS + goff], o2 = sm[2 * AS + goff];
       const size_t gi = eb + tid;
       if (flags & FLAG_ACCUM) {
-        p.f[0][gi] -= o0; p.f[1][gi] -= o1; p.f[2][gi] -= o2;
+        p.f[0][gi] = ep_f[0] - o0; p.f[1][gi] = ep_f[1] - o1; p.f[2][gi] = ep_f[2] - o2;
       } else {
         double f0 = 0.0, f1 = 0.0, f2 = 0.0;
         if (flags & (FLAG_SOURCES | FLAG_FSTATIC | FLAG_SENS)) {
-          const double pv0 = __ldg(p.v[0] + gi), pv1 = __ldg(p.v[1] + gi), pv2 = __ldg(p.v[2] + gi);
-          const double b0 = __ldg(p.vb[0] + gi), b1 = __ldg(p.vb[1] + gi), b2 = __ldg(p.vb[2] + gi);
-          const double bm = (flags & (FLAG_SOURCES | FLAG_FSTATIC)) ? __ldg(p.B + gi) : 0.0;
+          const double bm = ep_bm;
           if (flags & FLAG_SOURCES) {
-            double ch = __ldg(p.rho + gi);
+            double ch = ep_rho;
             if (flags & FLAG_RAMP) {
               if (flags & FLAG_CONVEX_UP) ch = p.f_min + (p.f_max - p.f_min) * ch * (1.0 + p.q) / (ch + p.q);
               else ch = p.f_min + (p.f_max - p.f_min) * ch / (1.0 + p.q * (1.0 - ch));

@@ -171,6 +171,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
         const bool isb = fo < 3;                       // base-flow fields first (twice the work)
         double* arr = sm + (isb ? 3 + fo : fo - 3) * AS + 12 * pg + PS * t;
         const double d0 = arr[q], d1 = arr[4 + q];
+        __syncwarp();                                  // in place: every lane has read before any lane stores
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           double c0 = 0.0, c1 = 0.0;
@@ -210,6 +211,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
         double* dr = sm + (6 + fo) * AS;
         double* ds = sm + (9 + fo) * AS;
         if (isb) { e0 = dr[lo]; e1 = dr[lo + 48]; }
+        __syncwarp();
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
           double c0 = 0.0, c1 = 0.0;
@@ -244,6 +246,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
           double* dt = sm + (12 + fo) * AS;
           const double d0 = arr[lo], d1 = arr[lo + 4 * PS];
           const double r0 = dr[lo], r1 = dr[lo + 4 * PS], s0 = ds[lo], s1 = ds[lo + 4 * PS];
+          __syncwarp();
 #pragma unroll
           for (int mt = 0; mt < 2; mt++) {
             double c0 = 0.0, c1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
@@ -267,6 +270,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
           double d0[3], d1[3];
 #pragma unroll
           for (int fo = 0; fo < 3; fo++) { d0[fo] = sm[fo * AS + lo]; d1[fo] = sm[fo * AS + lo + 4 * PS]; }
+          __syncwarp();
 #pragma unroll
           for (int mt = 0; mt < 2; mt++) {
             double c0[3] = {0.0, 0.0, 0.0}, c1[3] = {0.0, 0.0, 0.0};
@@ -355,6 +359,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
             x[ks] = R[lo + 4 * PS * ks]; y[ks] = Ft[lo + 4 * PS * ks];
             u[ks] = Fr[lo + 4 * PS * ks]; w[ks] = Fs[lo + 4 * PS * ks];
           }
+          __syncwarp();
           double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, h0 = 0.0, h1 = 0.0, k0 = 0.0, k1 = 0.0;
 #pragma unroll
           for (int ks = 0; ks < 3; ks++) {
@@ -399,6 +404,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
           double x[3], y[3];
 #pragma unroll
           for (int ks = 0; ks < 3; ks++) { x[ks] = R[lo + 48 * ks]; y[ks] = X3[lo + 48 * ks]; }
+          __syncwarp();
           double e0 = 0.0, e1 = 0.0;
 #pragma unroll
           for (int ks = 0; ks < 3; ks++) {
@@ -411,6 +417,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
           double x[3];
 #pragma unroll
           for (int ks = 0; ks < 3; ks++) x[ks] = X2[lo + 48 * ks];
+          __syncwarp();
 #pragma unroll
           for (int ks = 0; ks < 3; ks++) dmma884(c0, c1, jt[ks], x[ks]);
           st2(X2 + so, c0, c1);
@@ -431,6 +438,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
         double x[3], y[3];
 #pragma unroll
         for (int ks = 0; ks < 3; ks++) { x[ks] = R[4 * ks + q]; y[ks] = Y2[4 * ks + q]; }
+        __syncwarp();
         double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 3; ks++) {

@@ -20,6 +20,7 @@
 // Each product is evaluated axis by axis, IN PLACE in the arrays (a warp tile reads all the pencils of its 8 batch
 // entries before it stores them), sums that share the remaining axes are accumulated in the DMMA accumulators:
 //   F1 (r):  A1 = J_r q,  A2 = DJ_r U                      F2 (s):  B1 = J_s A1, B2 = DJ_s A1, B3 = J_s A2
+//            (A1 of the base flow goes to the d_t array, free until F3, so that F1 splits into 72 equal tasks)
 //   F3 (t):  T = J_t B1, d_t = DJ_t B1, d_s = J_t B2, d_r = J_t B3
 //   T1 (t):  X1 = J^T_t R + DJ^T_t Ft,  X2 = J^T_t Fr,  X3 = J^T_t Fs
 //   T2 (s):  Y1 = J^T_s X1 + DJ^T_s X3, Y2 = J^T_s X2      T3 (r):  out = J^T_r Y1 + DJ^T_r Y2
@@ -162,32 +163,24 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
     __syncthreads();
 
     // ---- F1: r axis.  batch (m, n): tile t = n, entry g = row m = pi(g); output a = 2q, 2q+1 (+8 nt): matrix as B ---
+    // 72 equal tasks (4 per warp): base flow A1 = J_r U -> DT array, A2 = DJ_r U -> DR array, adjoint velocity in place
     {
       double mj[4], md[4];
 #pragma unroll
       for (int x = 0; x < 4; x++) { mj[x] = FT[(14 + x) * 32 + lane]; md[x] = FT[(18 + x) * 32 + lane]; }
-      for (int tk = warp; tk < 48; tk += C::NWARP) {
-        const int fo = tk >> 3, t = tk & 7;
-        const bool isb = fo < 3;                       // base-flow fields first (twice the work)
-        double* arr = sm + (isb ? 3 + fo : fo - 3) * AS + 12 * pg + PS * t;
-        const double d0 = arr[q], d1 = arr[4 + q];
-        __syncwarp();                                  // in place: every lane has read before any lane stores
+      for (int tk = warp; tk < 72; tk += C::NWARP) {
+        const int kind = tk / 24, r = tk - 24 * kind, fo = r >> 3, t = r & 7;
+        const int ro = 12 * pg + PS * t;
+        const double* src = sm + (kind < 2 ? 3 + fo : fo) * AS + ro;
+        double* dst = sm + (kind == 0 ? 12 + fo : kind == 1 ? 6 + fo : fo) * AS + ro;
+        const double d0 = src[q], d1 = src[4 + q];
+        __syncwarp();                                  // in place (kind 2): every lane has read before any lane stores
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           double c0 = 0.0, c1 = 0.0;
-          dmma884(c0, c1, d0, mj[nt * 2 + 0]);
-          dmma884(c0, c1, d1, mj[nt * 2 + 1]);
-          if (nt == 0 || q < 2) st2(arr + 8 * nt + 2 * q, c0, c1);
-        }
-        if (isb) {
-          double* dr = sm + (6 + fo) * AS + 12 * pg + PS * t;
-#pragma unroll
-          for (int nt = 0; nt < 2; nt++) {
-            double c0 = 0.0, c1 = 0.0;
-            dmma884(c0, c1, d0, md[nt * 2 + 0]);
-            dmma884(c0, c1, d1, md[nt * 2 + 1]);
-            if (nt == 0 || q < 2) st2(dr + 8 * nt + 2 * q, c0, c1);
-          }
+          dmma884(c0, c1, d0, kind == 1 ? md[nt * 2 + 0] : mj[nt * 2 + 0]);
+          dmma884(c0, c1, d1, kind == 1 ? md[nt * 2 + 1] : mj[nt * 2 + 1]);
+          if (nt == 0 || q < 2) st2(dst + 8 * nt + 2 * q, c0, c1);
         }
       }
     }
@@ -199,18 +192,42 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
       for (int x = 0; x < 4; x++) { mj[x] = FT[x * 32 + lane]; md[x] = FT[(4 + x) * 32 + lane]; }
 
       // ---- F2: s axis.  batch beta = a + 12 n (96); output b = pi(g) (+8 mt): matrix as A ---------------------------
-      for (int tk = warp; tk < 72; tk += C::NWARP) {
+      // base flow (2 tasks per warp): B1 = J_s A1 -> TB, B2 = DJ_s A1 -> DS, B3 = J_s A2 -> DR (in place)
+      for (int tk = warp; tk < 36; tk += C::NWARP) {
         const int fo = tk / 12, t = tk - 12 * fo;
-        const bool isb = fo < 3;
         const int bl = 8 * t + g, bs = 8 * t + 2 * q;                 // load / store batch entry
         const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;           // + 48 per k-step
         const int so = (bs % 12) + PS * (bs / 12) + 12 * pg;          // + 96 for mt = 1
-        double* arr = sm + (isb ? 3 + fo : fo - 3) * AS;
-        const double d0 = arr[lo], d1 = arr[lo + 48];
-        double e0 = 0.0, e1 = 0.0;
+        double* tb = sm + (3 + fo) * AS;
         double* dr = sm + (6 + fo) * AS;
         double* ds = sm + (9 + fo) * AS;
-        if (isb) { e0 = dr[lo]; e1 = dr[lo + 48]; }
+        const double* a1 = sm + (12 + fo) * AS;
+        const double d0 = a1[lo], d1 = a1[lo + 48], e0 = dr[lo], e1 = dr[lo + 48];
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          double c0 = 0.0, c1 = 0.0, b0 = 0.0, b1 = 0.0, a0 = 0.0, a1v = 0.0;
+          dmma884(c0, c1, mj[mt * 2], d0);
+          dmma884(b0, b1, md[mt * 2], d0);
+          dmma884(a0, a1v, mj[mt * 2], e0);
+          dmma884(c0, c1, mj[mt * 2 + 1], d1);
+          dmma884(b0, b1, md[mt * 2 + 1], d1);
+          dmma884(a0, a1v, mj[mt * 2 + 1], e1);
+          if (mt == 0 || g < 4) {
+            st2(tb + so + 96 * mt, c0, c1);
+            st2(ds + so + 96 * mt, b0, b1);
+            st2(dr + so + 96 * mt, a0, a1v);
+          }
+        }
+      }
+      // adjoint velocity (2 tasks per warp): in place
+      for (int tk = warp; tk < 36; tk += C::NWARP) {
+        const int fo = tk / 12, t = tk - 12 * fo;
+        const int bl = 8 * t + g, bs = 8 * t + 2 * q;
+        const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;
+        const int so = (bs % 12) + PS * (bs / 12) + 12 * pg;
+        double* arr = sm + fo * AS;
+        const double d0 = arr[lo], d1 = arr[lo + 48];
         __syncwarp();
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
@@ -218,14 +235,6 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
           dmma884(c0, c1, mj[mt * 2], d0);
           dmma884(c0, c1, mj[mt * 2 + 1], d1);
           if (mt == 0 || g < 4) st2(arr + so + 96 * mt, c0, c1);
-          if (isb) {
-            double b0 = 0.0, b1 = 0.0, a0 = 0.0, a1 = 0.0;
-            dmma884(b0, b1, md[mt * 2], d0);
-            dmma884(b0, b1, md[mt * 2 + 1], d1);
-            dmma884(a0, a1, mj[mt * 2], e0);
-            dmma884(a0, a1, mj[mt * 2 + 1], e1);
-            if (mt == 0 || g < 4) { st2(ds + so + 96 * mt, b0, b1); st2(dr + so + 96 * mt, a0, a1); }
-          }
         }
       }
       __syncthreads();

@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dealias", action="store_true", help="skip the extra dealiased-operator leg (N = 1, lx = 8)")
+    ap.add_argument("--dealias-ne", type=int, default=32)
     ap.add_argument("--cpu-sample-ne", type=int, default=16)
     return ap.parse_args()
 
@@ -209,6 +211,59 @@ def parity_vs_oracle(prob, f_dev, sens_dev, ne_gpu, oracle_out=None, tol=1e-12):
             "ok": bool(np.isfinite(worst) and worst <= tol),
             "against": "oracle/oracle.c on the " + prob["desc"] + "; f after gs on the nodes whose class lies inside "
                        "the sample, sens on all of it"}
+
+
+def dealiased_leg(ne, lx, dev, steps=10, sample_nel=256, tol=1e-12):
+    """Extra (N = 1): the same step with the DEALIASED adjoint operator (case.numerics.dealias = true, what the reference's
+    shipped lx = 8 cases run) on an ne^3 box -- device-resident step time, and the fused right-hand side
+    of the first `sample_nel` elements against oracle.c's dealiased operator."""
+    import numpy as np
+    import torch
+    from neko_top_b200 import operators as ops, sem, workloads
+    from oracle import pyoracle
+    brick = workloads.config_box(ne, lx)
+    sp = sem.Space(lx)
+    x, y, z = workloads.coords(brick, dev)
+    keys = workloads.node_keys(brick, dev)
+    G, _, B = sem.geometric_factors(x, y, z, sp, chunk=8192)
+    fl = workloads.make_fields(brick, x, y, z, keys)
+    flat = lambda a: a.reshape(-1).contiguous()
+    G, B = [flat(g) for g in G], flat(B)
+    v, ub, rho = [flat(a) for a in fl.v], [flat(a) for a in fl.ub], flat(fl.rho)
+    n = brick.n
+    f = [torch.empty(n, device=dev, dtype=torch.float64) for _ in range(3)]
+    sens = torch.empty(n, device=dev, dtype=torch.float64)
+    op = ops.fused_adjoint_rhs_t(ops.coef_t(ops.space_t(lx, sp.dx, sp.wx), brick.nelv, G, B), device=dev.index)
+    op.set_params()
+    op.gs.init(flat(keys))
+    lxd = 3 * lx // 2
+    op.set_dealias(True)
+    # parity of the element kernel (no summation) on a sample
+    op.compute(v, ub, f, rho=rho, sens=sens)
+    m = sample_nel * lx ** 3
+    c = lambda t: t[:m].cpu().numpy()
+    fo, so, _ = pyoracle.adjoint_rhs([c(a) for a in v], [c(a) for a in ub], lx, sample_nel, sp.dx,
+                                     sp.wx, [c(g) for g in G], c(B), rho=c(rho), lxd=lxd)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    err_f = max(rel(c(f[k]), fo[k]) for k in range(3))
+    err_s = rel(c(sens), so)
+    for _ in range(3):
+        op.step(v, ub, f, rho=rho, sens=sens)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        op.step(v, ub, f, rho=rho, sens=sens)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    op.free()
+    return {"value": n / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "workload": f"{ne}^3-element box, lx={lx}, lxd={lxd} (dealiased adjoint operator + Brinkman + sensitivity + "
+                        "direct-stiffness summation)",
+            "kernel": "advop_mma_kernel (FP64 tensor cores, mma.sync.m8n8k4.f64)" if lx == 8 else "advop_kernel",
+            "parity": {"rel_l2_f": err_f, "rel_l2_sens": err_s, "tol": tol, "ok": bool(err_f <= tol and err_s <= tol),
+                       "sample": f"first {sample_nel} elements, fused right-hand side vs oracle/oracle.c (lxd={lxd})"}}
 
 
 def run_reference(args):
@@ -462,6 +517,13 @@ def run_b200(args):
         # ---- parity of THIS run's result (every N): the last timed step against the oracle ------------
         parity = parity_vs_oracle(prob, f, sens, ne, oracle_out=kept or None)
 
+    dealiased = None
+    if rank == 0 and N == 1 and lx == 8 and not args.no_dealias:
+        try:
+            dealiased = dealiased_leg(args.dealias_ne, lx, dev)
+        except Exception as ex:           # an extra: never takes the headline line down
+            dealiased = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         line = {
             "metric": METRIC if lx == 8 else METRIC.replace("lx=8", f"lx={lx}"), "value": value, "unit": UNIT,
@@ -472,6 +534,8 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity, "clocks": clk.summary(), "checksum_abs_f": checksum, "host_cpus_bound": numa,
         }
+        if dealiased is not None:
+            line["dealiased"] = dealiased
         if phases:
             names = (["boundary_elements", "shared_gs", "pack", "interior_elements", "local_gs", "wait_recv+unpack"]
                      if os.environ.get("B200_EXCHANGE_OVERLAP") == "elem" else

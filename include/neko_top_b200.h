@@ -126,7 +126,9 @@ int b200_adv_linear_compute(void* handle,
  * adjoint/advection_adjoint_fctry.f90:70,89 -- is instantiated; anything else is an error. */
 int b200_adv_dealias_init(void* handle, const int* lxd, const double* interp, const double* dxd,
                           const double* wd);
-/* adv_lin_dealias_t%compute_adjoint (adjoint/adv_adjoint_dealias.f90:235-462); f IN/OUT. */
+/* adv_lin_dealias_t%compute_adjoint (adjoint/adv_adjoint_dealias.f90:235-462); f IN/OUT.
+ * lx = 8 / lxd = 12 runs on the FP64 tensor cores (csrc/advop_mma_kernel.cuh; environment B200_ADVOP_MMA=0 selects
+ * the column-per-thread kernel the other orders use); same interface, same 1e-12 parity. */
 int b200_adv_adjoint_dealias_compute(void* handle,
                                      const void* vx, const void* vy, const void* vz,
                                      const void* vxb, const void* vyb, const void* vzb,

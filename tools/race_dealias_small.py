@@ -1,5 +1,7 @@
+"""Fused dealiased step at lx = 8 on 4 elements, for `compute-sanitizer --tool racecheck` (advop_mma_kernel's in-place
+shared-memory GEMM tiles)."""
 import os, sys
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from helpers import Problem

@@ -24,7 +24,8 @@
 //   F3 (t):  T = J_t B1, d_t = DJ_t B1, d_s = J_t B2, d_r = J_t B3
 //   T1 (t):  X1 = J^T_t R + DJ^T_t Ft,  X2 = J^T_t Fr,  X3 = J^T_t Fs
 //   T2 (s):  Y1 = J^T_s X1 + DJ^T_s X3, Y2 = J^T_s X2      T3 (r):  out = J^T_r Y1 + DJ^T_r Y2
-// 3060 DMMAs per element (75 % useful forward: 12 outputs in two 8-row tiles; 100 % backward) against 750 k DFMAs.
+// 2880 DMMAs per element (forward: 12 outputs in two 8-row tiles, the leftover rows of J and DJ stacked into one tile
+// where they multiply the same data; 100 % useful backward) against 750 k DFMAs.
 //
 // Fragments (PTX m8n8k4, lane = 4 g + q): A(row g, col q), B(row q, col g), C(row g, cols 2q, 2q+1).  The DATA
 // fragment of a tile is always "contraction index 4 ks + q of batch entry g", whichever operand it is; the MATRIX
@@ -74,8 +75,9 @@ struct AdvMmaCfg {
   static constexpr int PS = 148;                  // plane stride in shared memory
   static constexpr int AS = LXD * PS;             // array stride
   static constexpr int NARR = 15;                 // TV 0..2, TB 3..5, DR 6..8, DS 9..11, DT 12..14
-  static constexpr int NFRAG = 28;                // J: 0..3 (mt*2+ks), DJ: 4..7, J^T: 8..10 (ks), DJ^T: 11..13 with output row
-                                                  // pi(g) (matrix as A); 14..27: the same with output row g (matrix as B)
+  static constexpr int NFRAG = 30;                // J: 0..3 (mt*2+ks), DJ: 4..7, J^T: 8..10 (ks), DJ^T: 11..13 with output row
+                                                  // pi(g) (matrix as A); 14..27: the same with output row g (matrix as B);
+                                                  // 28, 29 (ks): rows pi(g) < 4 -> J row 8 + pi(g), else DJ row 4 + pi(g)
   static constexpr int FT_OFF = NARR * AS;
   static constexpr int W_OFF = FT_OFF + NFRAG * 32;
   static constexpr int SMEM = (W_OFF + 12) * 8;          // 220.4 KB
@@ -124,9 +126,12 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
   for (int idx = tid; idx < C::NFRAG * 32; idx += C::NTHR) {
     const int fr = idx >> 5, gg0 = (idx & 31) >> 2, qq = idx & 3;
     const int fid = fr % 14;
-    const int gg = (fr < 14) ? ((gg0 & 4) | ((gg0 & 1) << 1) | ((gg0 >> 1) & 1)) : gg0;
+    const int gg = (fr < 14 || fr >= 28) ? ((gg0 & 4) | ((gg0 & 1) << 1) | ((gg0 >> 1) & 1)) : gg0;
     double val;
-    if (fid < 8) {                     // forward: M(output a = 8 mt + row, contraction l = 4 ks + q), rows >= 12 are zero
+    if (fr >= 28) {                    // the four leftover rows of J and of DJ in one 8-row tile (they multiply the same data)
+      const int c = 4 * (fr - 28) + qq;
+      val = (gg < 4) ? p.J[8 + gg + 12 * c] : p.DJ[4 + gg + 12 * c];
+    } else if (fid < 8) {                     // forward: M(output a = 8 mt + row, contraction l = 4 ks + q), rows >= 12 are zero
       const int mt = (fid & 3) >> 1, ks = fid & 1, o = 8 * mt + gg, c = 4 * ks + qq;
       val = (o < 12) ? (fid < 4 ? p.J[o + 12 * c] : p.DJ[o + 12 * c]) : 0.0;
     } else {                           // backward: M(output l = row, contraction a = 4 ks + q) = J(a, l)
@@ -190,6 +195,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
       double mj[4], md[4];     // J, DJ as A operand with output row pi(g): [mt*2 + ks]
 #pragma unroll
       for (int x = 0; x < 4; x++) { mj[x] = FT[x * 32 + lane]; md[x] = FT[(4 + x) * 32 + lane]; }
+      const double mh[2] = {FT[28 * 32 + lane], FT[29 * 32 + lane]};   // stacked leftover rows of J and DJ
 
       // ---- F2: s axis.  batch beta = a + 12 n (96); output b = pi(g) (+8 mt): matrix as A ---------------------------
       // base flow (2 tasks per warp): B1 = J_s A1 -> TB, B2 = DJ_s A1 -> DS, B3 = J_s A2 -> DR (in place)
@@ -204,20 +210,26 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
         const double* a1 = sm + (12 + fo) * AS;
         const double d0 = a1[lo], d1 = a1[lo + 48], e0 = dr[lo], e1 = dr[lo + 48];
         __syncwarp();
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
+        {                                                             // rows 0..7
           double c0 = 0.0, c1 = 0.0, b0 = 0.0, b1 = 0.0, a0 = 0.0, a1v = 0.0;
-          dmma884(c0, c1, mj[mt * 2], d0);
-          dmma884(b0, b1, md[mt * 2], d0);
-          dmma884(a0, a1v, mj[mt * 2], e0);
-          dmma884(c0, c1, mj[mt * 2 + 1], d1);
-          dmma884(b0, b1, md[mt * 2 + 1], d1);
-          dmma884(a0, a1v, mj[mt * 2 + 1], e1);
-          if (mt == 0 || g < 4) {
-            st2(tb + so + 96 * mt, c0, c1);
-            st2(ds + so + 96 * mt, b0, b1);
-            st2(dr + so + 96 * mt, a0, a1v);
-          }
+          dmma884(c0, c1, mj[0], d0);
+          dmma884(b0, b1, md[0], d0);
+          dmma884(a0, a1v, mj[0], e0);
+          dmma884(c0, c1, mj[1], d1);
+          dmma884(b0, b1, md[1], d1);
+          dmma884(a0, a1v, mj[1], e1);
+          st2(tb + so, c0, c1);
+          st2(ds + so, b0, b1);
+          st2(dr + so, a0, a1v);
+        }
+        {                                                             // rows 8..11: J A1 and DJ A1 share one stacked tile
+          double h0 = 0.0, h1 = 0.0, a0 = 0.0, a1v = 0.0;
+          dmma884(h0, h1, mh[0], d0);
+          dmma884(a0, a1v, mj[2], e0);
+          dmma884(h0, h1, mh[1], d1);
+          dmma884(a0, a1v, mj[3], e1);
+          st2((g < 4 ? tb + 96 : ds + 48) + so, h0, h1);              // g >= 4: pi(g) = 4 + r -> row 8 + r = pi(g) + 4
+          if (g < 4) st2(dr + so + 96, a0, a1v);
         }
       }
       // adjoint velocity (2 tasks per warp): in place
@@ -241,7 +253,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
 
       // ---- F3 -> point-wise -> T1 on one tile of 8 (i,j) columns per warp, no CTA barrier in between: the t-axis stages
       // and the point-wise work only couple the 12 planes of a column, so a warp carries its 96 points through all
-      // three, and the warps drift apart -- tensor-core, FP64 and load phases of different warps overlap.
+      // three.  (The warps stay roughly in phase, which is what the FP64 pipe wants: DFMA and DMMA alternate badly.)
       // F3: t axis.  batch beta = a + 12 b (contiguous); output c = pi(g) (+8 mt): matrix as A
       const int t = warp;
       {
@@ -256,22 +268,33 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
           const double d0 = arr[lo], d1 = arr[lo + 4 * PS];
           const double r0 = dr[lo], r1 = dr[lo + 4 * PS], s0 = ds[lo], s1 = ds[lo + 4 * PS];
           __syncwarp();
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++) {
+          {                                                           // planes 0..7
             double c0 = 0.0, c1 = 0.0, t0 = 0.0, t1 = 0.0, a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-            dmma884(c0, c1, mj[mt * 2], d0);
-            dmma884(t0, t1, md[mt * 2], d0);
-            dmma884(a0, a1, mj[mt * 2], s0);
-            dmma884(b0, b1, mj[mt * 2], r0);
-            dmma884(c0, c1, mj[mt * 2 + 1], d1);
-            dmma884(t0, t1, md[mt * 2 + 1], d1);
-            dmma884(a0, a1, mj[mt * 2 + 1], s1);
-            dmma884(b0, b1, mj[mt * 2 + 1], r1);
-            if (mt == 0 || g < 4) {
-              st2(arr + so + 8 * PS * mt, c0, c1);
-              st2(dt + so + 8 * PS * mt, t0, t1);
-              st2(ds + so + 8 * PS * mt, a0, a1);
-              st2(dr + so + 8 * PS * mt, b0, b1);
+            dmma884(c0, c1, mj[0], d0);
+            dmma884(t0, t1, md[0], d0);
+            dmma884(a0, a1, mj[0], s0);
+            dmma884(b0, b1, mj[0], r0);
+            dmma884(c0, c1, mj[1], d1);
+            dmma884(t0, t1, md[1], d1);
+            dmma884(a0, a1, mj[1], s1);
+            dmma884(b0, b1, mj[1], r1);
+            st2(arr + so, c0, c1);
+            st2(dt + so, t0, t1);
+            st2(ds + so, a0, a1);
+            st2(dr + so, b0, b1);
+          }
+          {                                                           // planes 8..11: T and d_t share one stacked tile
+            double h0 = 0.0, h1 = 0.0, a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            dmma884(h0, h1, mh[0], d0);
+            dmma884(a0, a1, mj[2], s0);
+            dmma884(b0, b1, mj[2], r0);
+            dmma884(h0, h1, mh[1], d1);
+            dmma884(a0, a1, mj[3], s1);
+            dmma884(b0, b1, mj[3], r1);
+            st2((g < 4 ? arr + 8 * PS : dt + 4 * PS) + so, h0, h1);   // g >= 4: plane 8 + r = pi(g) + 4
+            if (g < 4) {
+              st2(ds + so + 8 * PS, a0, a1);
+              st2(dr + so + 8 * PS, b0, b1);
             }
           }
         }

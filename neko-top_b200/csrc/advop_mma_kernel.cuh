@@ -6,8 +6,8 @@
 // per element; ncu r02h: issue 25 %, fp64 pipe 26 %, 45 % of the shared-memory wavefront peak) because every DFMA of
 // an r/s contraction needs its own shared-memory operand.  A DMMA takes one 64-bit fragment load per 256 FMAs, needs
 // ~60 registers per warp instead of 168, and so 18 warps share one SM with the whole element (15 fine-grid arrays)
-// in shared memory.  Measured (profiles/r02D): fused dealiased step 6.56 -> 3.08 ms at 32^3 elements (2.56 -> 5.45
-// GDOF/s), un-fused drop-in 5.80 -> 3.02 ms.
+// in shared memory.  Measured (profiles/r02D, r02G): fused dealiased step 6.55 -> 2.93 ms at 32^3 elements (2.56 -> 5.73
+// GDOF/s), un-fused drop-in 5.77 -> 2.86 ms.
 //
 // Formulation.  With J (12x8) the GLL -> Gauss-Legendre interpolation, D (12x12) the fine-grid derivative and
 // DJ = D J (12x8, formed on the host), per element:
@@ -41,7 +41,7 @@
 // the epilogue's inputs and the next element's fields are loaded two stages early with volatile loads; the fine-grid
 // geometry of the element is prefetched into L2 when the element starts.  ncu (r02D5): DMMA pipe 45 % busy, shared-
 // memory wavefronts 43 %; the rest is the point-wise phase (21 %, LSU-bound: 27 shared + 9 global accesses per point)
-// and barrier waits (18 %: 18 tiles over 4 schedulers, 48 / 24 tasks over 18 warps in F1 / T3).
+// and barrier waits (18 %: 18 tiles over 4 schedulers, 24 tasks over 18 warps in T3).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

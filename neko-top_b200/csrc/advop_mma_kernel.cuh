@@ -173,18 +173,24 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
       double mj[4], md[4];
 #pragma unroll
       for (int x = 0; x < 4; x++) { mj[x] = FT[(14 + x) * 32 + lane]; md[x] = FT[(18 + x) * 32 + lane]; }
-      for (int tk = warp; tk < 72; tk += C::NWARP) {
-        const int kind = tk / 24, r = tk - 24 * kind, fo = r >> 3, t = r & 7;
-        const int ro = 12 * pg + PS * t;
-        const double* src = sm + (kind < 2 ? 3 + fo : fo) * AS + ro;
-        double* dst = sm + (kind == 0 ? 12 + fo : kind == 1 ? 6 + fo : fo) * AS + ro;
-        const double d0 = src[q], d1 = src[4 + q];
-        __syncwarp();                                  // in place (kind 2): every lane has read before any lane stores
+      // the four tasks of a warp: all fragment loads first, then the DMMAs (short dependent chains otherwise)
+      double d0[4], d1[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int tk = warp + C::NWARP * j, kind = tk / 24, r = tk - 24 * kind, fo = r >> 3, t = r & 7;
+        const double* src = sm + (kind < 2 ? 3 + fo : fo) * AS + 12 * pg + PS * t;
+        d0[j] = src[q]; d1[j] = src[4 + q];
+      }
+      __syncwarp();                                    // in place (kind 2): every lane has read before any lane stores
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int tk = warp + C::NWARP * j, kind = tk / 24, r = tk - 24 * kind, fo = r >> 3, t = r & 7;
+        double* dst = sm + (kind == 0 ? 12 + fo : kind == 1 ? 6 + fo : fo) * AS + 12 * pg + PS * t;
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           double c0 = 0.0, c1 = 0.0;
-          dmma884(c0, c1, d0, kind == 1 ? md[nt * 2 + 0] : mj[nt * 2 + 0]);
-          dmma884(c0, c1, d1, kind == 1 ? md[nt * 2 + 1] : mj[nt * 2 + 1]);
+          dmma884(c0, c1, d0[j], kind == 1 ? md[nt * 2 + 0] : mj[nt * 2 + 0]);
+          dmma884(c0, c1, d1[j], kind == 1 ? md[nt * 2 + 1] : mj[nt * 2 + 1]);
           if (nt == 0 || q < 2) st2(dst + 8 * nt + 2 * q, c0, c1);
         }
       }
@@ -424,35 +430,38 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
       }
 
       // ---- T2: s axis, K = 12.  batch beta = i + 12 n (96); output m = pi(g).  part 0: Y1 -> R, part 1: Y2 -> Fr -----
-      for (int tk = warp; tk < 72; tk += C::NWARP) {
-        const int c = tk / 24, r = tk - 24 * c, t = r >> 1, part = r & 1;
-        const int bl = 8 * t + g, bs = 8 * t + 2 * q;
-        const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;            // + 48 per k-step
-        const int so = (bs % 12) + PS * (bs / 12) + 12 * pg;
-        double c0 = 0.0, c1 = 0.0;
-        if (part == 0) {
-          double* R = sm + c * AS;
-          const double* X3 = sm + (9 + c) * AS;
-          double x[3], y[3];
+      // 36 (component, tile) pairs x {Y1: 6 DMMAs, Y2: 3}: every warp takes two pairs whole (18 DMMAs each warp), all
+      // fragment loads first
+      {
+        double x[2][3], y[2][3], u[2][3];
+        int lo[2], so[2], cc[2];
 #pragma unroll
-          for (int ks = 0; ks < 3; ks++) { x[ks] = R[lo + 48 * ks]; y[ks] = X3[lo + 48 * ks]; }
-          __syncwarp();
-          double e0 = 0.0, e1 = 0.0;
+        for (int j = 0; j < 2; j++) {
+          const int idx = warp + C::NWARP * j, c = idx / 12, t = idx - 12 * c;
+          const int bl = 8 * t + g, bs = 8 * t + 2 * q;
+          cc[j] = c;
+          lo[j] = (bl % 12) + PS * (bl / 12) + 12 * q;               // + 48 per k-step
+          so[j] = (bs % 12) + PS * (bs / 12) + 12 * pg;
+          const double* R = sm + c * AS;
+          const double* X2 = sm + (6 + c) * AS;
+          const double* X3 = sm + (9 + c) * AS;
 #pragma unroll
           for (int ks = 0; ks < 3; ks++) {
-            dmma884(c0, c1, jt[ks], x[ks]);
-            dmma884(e0, e1, djt[ks], y[ks]);
+            x[j][ks] = R[lo[j] + 48 * ks]; y[j][ks] = X3[lo[j] + 48 * ks]; u[j][ks] = X2[lo[j] + 48 * ks];
           }
-          st2(R + so, c0 + e0, c1 + e1);
-        } else {
-          double* X2 = sm + (6 + c) * AS;
-          double x[3];
+        }
+        __syncwarp();
 #pragma unroll
-          for (int ks = 0; ks < 3; ks++) x[ks] = X2[lo + 48 * ks];
-          __syncwarp();
+        for (int j = 0; j < 2; j++) {
+          double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
-          for (int ks = 0; ks < 3; ks++) dmma884(c0, c1, jt[ks], x[ks]);
-          st2(X2 + so, c0, c1);
+          for (int ks = 0; ks < 3; ks++) {
+            dmma884(c0, c1, jt[ks], x[j][ks]);
+            dmma884(e0, e1, djt[ks], y[j][ks]);
+            dmma884(h0, h1, jt[ks], u[j][ks]);
+          }
+          st2(sm + cc[j] * AS + so[j], c0 + e0, c1 + e1);
+          st2(sm + (6 + cc[j]) * AS + so[j], h0, h1);
         }
       }
     }
@@ -463,21 +472,26 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
       double jt[3], djt[3];
 #pragma unroll
       for (int ks = 0; ks < 3; ks++) { jt[ks] = FT[(22 + ks) * 32 + lane]; djt[ks] = FT[(25 + ks) * 32 + lane]; }
-      for (int tk = warp; tk < 24; tk += 12) {
-        const int c = tk >> 3, t = tk & 7;
-        double* R = sm + c * AS + 12 * pg + PS * t;
-        const double* Y2 = sm + (6 + c) * AS + 12 * pg + PS * t;
-        double x[3], y[3];
+      double x[2][3], y[2][3];
 #pragma unroll
-        for (int ks = 0; ks < 3; ks++) { x[ks] = R[4 * ks + q]; y[ks] = Y2[4 * ks + q]; }
-        __syncwarp();
+      for (int j = 0; j < 2; j++) {
+        const int tk = warp + 12 * j, c = tk >> 3, t = tk & 7;
+        const double* R = sm + c * AS + 12 * pg + PS * t;
+        const double* Y2 = sm + (6 + c) * AS + 12 * pg + PS * t;
+#pragma unroll
+        for (int ks = 0; ks < 3; ks++) { x[j][ks] = R[4 * ks + q]; y[j][ks] = Y2[4 * ks + q]; }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int tk = warp + 12 * j, c = tk >> 3, t = tk & 7;
         double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 3; ks++) {
-          dmma884(c0, c1, x[ks], jt[ks]);
-          dmma884(e0, e1, y[ks], djt[ks]);
+          dmma884(c0, c1, x[j][ks], jt[ks]);
+          dmma884(e0, e1, y[j][ks], djt[ks]);
         }
-        st2(R + 2 * q, c0 + e0, c1 + e1);
+        st2(sm + c * AS + 12 * pg + PS * t + 2 * q, c0 + e0, c1 + e1);
       }
     }
     __syncthreads();

@@ -204,55 +204,57 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
       const double mh[2] = {FT[28 * 32 + lane], FT[29 * 32 + lane]};   // stacked leftover rows of J and DJ
 
       // ---- F2: s axis.  batch beta = a + 12 n (96); output b = pi(g) (+8 mt): matrix as A ---------------------------
-      // base flow (2 tasks per warp): B1 = J_s A1 -> TB, B2 = DJ_s A1 -> DS, B3 = J_s A2 -> DR (in place)
-      for (int tk = warp; tk < 36; tk += C::NWARP) {
-        const int fo = tk / 12, t = tk - 12 * fo;
-        const int bl = 8 * t + g, bs = 8 * t + 2 * q;                 // load / store batch entry
-        const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;           // + 48 per k-step
-        const int so = (bs % 12) + PS * (bs / 12) + 12 * pg;          // + 96 for mt = 1
-        double* tb = sm + (3 + fo) * AS;
-        double* dr = sm + (6 + fo) * AS;
-        double* ds = sm + (9 + fo) * AS;
-        const double* a1 = sm + (12 + fo) * AS;
-        const double d0 = a1[lo], d1 = a1[lo + 48], e0 = dr[lo], e1 = dr[lo + 48];
-        __syncwarp();
-        {                                                             // rows 0..7
-          double c0 = 0.0, c1 = 0.0, b0 = 0.0, b1 = 0.0, a0 = 0.0, a1v = 0.0;
-          dmma884(c0, c1, mj[0], d0);
-          dmma884(b0, b1, md[0], d0);
-          dmma884(a0, a1v, mj[0], e0);
-          dmma884(c0, c1, mj[1], d1);
-          dmma884(b0, b1, md[1], d1);
-          dmma884(a0, a1v, mj[1], e1);
-          st2(tb + so, c0, c1);
-          st2(ds + so, b0, b1);
-          st2(dr + so, a0, a1v);
+      // per warp 2 base-flow tasks (B1 = J_s A1 -> TB, B2 = DJ_s A1 -> DS, B3 = J_s A2 -> DR in place) and 2 adjoint-velocity
+      // tasks (in place); all fragment loads first
+      {
+        double d0[2], d1[2], e0[2], e1[2], v0[2], v1[2];
+        int so[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const int tk = warp + C::NWARP * j, fo = tk / 12, t = tk - 12 * fo;
+          const int bl = 8 * t + g, bs = 8 * t + 2 * q;               // load / store batch entry
+          const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;         // + 48 per k-step
+          so[j] = (bs % 12) + PS * (bs / 12) + 12 * pg;               // + 96 for mt = 1
+          const double* a1 = sm + (12 + fo) * AS;
+          const double* dr = sm + (6 + fo) * AS;
+          const double* tv = sm + fo * AS;
+          d0[j] = a1[lo]; d1[j] = a1[lo + 48]; e0[j] = dr[lo]; e1[j] = dr[lo + 48];
+          v0[j] = tv[lo]; v1[j] = tv[lo + 48];
         }
-        {                                                             // rows 8..11: J A1 and DJ A1 share one stacked tile
-          double h0 = 0.0, h1 = 0.0, a0 = 0.0, a1v = 0.0;
-          dmma884(h0, h1, mh[0], d0);
-          dmma884(a0, a1v, mj[2], e0);
-          dmma884(h0, h1, mh[1], d1);
-          dmma884(a0, a1v, mj[3], e1);
-          st2((g < 4 ? tb + 96 : ds + 48) + so, h0, h1);              // g >= 4: pi(g) = 4 + r -> row 8 + r = pi(g) + 4
-          if (g < 4) st2(dr + so + 96, a0, a1v);
-        }
-      }
-      // adjoint velocity (2 tasks per warp): in place
-      for (int tk = warp; tk < 36; tk += C::NWARP) {
-        const int fo = tk / 12, t = tk - 12 * fo;
-        const int bl = 8 * t + g, bs = 8 * t + 2 * q;
-        const int lo = (bl % 12) + PS * (bl / 12) + 12 * q;
-        const int so = (bs % 12) + PS * (bs / 12) + 12 * pg;
-        double* arr = sm + fo * AS;
-        const double d0 = arr[lo], d1 = arr[lo + 48];
         __syncwarp();
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-          double c0 = 0.0, c1 = 0.0;
-          dmma884(c0, c1, mj[mt * 2], d0);
-          dmma884(c0, c1, mj[mt * 2 + 1], d1);
-          if (mt == 0 || g < 4) st2(arr + so + 96 * mt, c0, c1);
+        for (int j = 0; j < 2; j++) {
+          const int tk = warp + C::NWARP * j, fo = tk / 12;
+          double* tb = sm + (3 + fo) * AS + so[j];
+          double* dr = sm + (6 + fo) * AS + so[j];
+          double* ds = sm + (9 + fo) * AS + so[j];
+          double* tv = sm + fo * AS + so[j];
+          {                                                           // rows 0..7
+            double c0 = 0.0, c1 = 0.0, b0 = 0.0, b1 = 0.0, a0 = 0.0, a1v = 0.0, w0 = 0.0, w1 = 0.0;
+            dmma884(c0, c1, mj[0], d0[j]);
+            dmma884(b0, b1, md[0], d0[j]);
+            dmma884(a0, a1v, mj[0], e0[j]);
+            dmma884(w0, w1, mj[0], v0[j]);
+            dmma884(c0, c1, mj[1], d1[j]);
+            dmma884(b0, b1, md[1], d1[j]);
+            dmma884(a0, a1v, mj[1], e1[j]);
+            dmma884(w0, w1, mj[1], v1[j]);
+            st2(tb, c0, c1);
+            st2(ds, b0, b1);
+            st2(dr, a0, a1v);
+            st2(tv, w0, w1);
+          }
+          {                                                           // rows 8..11: J A1 and DJ A1 share one stacked tile
+            double h0 = 0.0, h1 = 0.0, a0 = 0.0, a1v = 0.0, w0 = 0.0, w1 = 0.0;
+            dmma884(h0, h1, mh[0], d0[j]);
+            dmma884(a0, a1v, mj[2], e0[j]);
+            dmma884(w0, w1, mj[2], v0[j]);
+            dmma884(h0, h1, mh[1], d1[j]);
+            dmma884(a0, a1v, mj[3], e1[j]);
+            dmma884(w0, w1, mj[3], v1[j]);
+            st2(g < 4 ? tb + 96 : ds + 48, h0, h1);                   // g >= 4: pi(g) = 4 + r -> row 8 + r = pi(g) + 4
+            if (g < 4) { st2(dr + 96, a0, a1v); st2(tv + 96, w0, w1); }
+          }
         }
       }
       __syncthreads();

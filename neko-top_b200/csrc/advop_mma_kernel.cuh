@@ -6,8 +6,8 @@
 // per element; ncu r02h: issue 25 %, fp64 pipe 26 %, 45 % of the shared-memory wavefront peak) because every DFMA of
 // an r/s contraction needs its own shared-memory operand.  A DMMA takes one 64-bit fragment load per 256 FMAs, needs
 // ~60 registers per warp instead of 168, and so 18 warps share one SM with the whole element (15 fine-grid arrays)
-// in shared memory.  Measured (profiles/r02D, r02G): fused dealiased step 6.55 -> 2.93 ms at 32^3 elements (2.56 -> 5.73
-// GDOF/s), un-fused drop-in 5.77 -> 2.86 ms.
+// in shared memory.  Measured (profiles/r02D, r02G, r02J): fused dealiased step 6.55 -> 2.75 ms at 32^3 elements (2.56 ->
+// 6.10 GDOF/s), un-fused drop-in 5.77 -> 2.68 ms.
 //
 // Formulation.  With J (12x8) the GLL -> Gauss-Legendre interpolation, D (12x12) the fine-grid derivative and
 // DJ = D J (12x8, formed on the host), per element:

@@ -148,40 +148,35 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
 
   auto elem_of = [&](int it) { return p.elem_list ? __ldg(p.elem_list + it) : p.elem_base + it; };
   const bool gth = tid < N;          // threads that own a GLL point
-  double un[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if ((int)blockIdx.x < p.nelem && gth) {
-    const size_t eb = (size_t)elem_of(blockIdx.x) * N + tid;
+  // F1's data fragments come straight from global memory, loaded one element ahead: task j of this warp (tk = warp +
+  // 18 j -> kind, field fo, plane t) needs l = q, 4 + q of row m = pi(g) of plane t
+  double uf0[4], uf1[4];
+  auto load_f1_fragments = [&](size_t ebase) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) { un[c] = __ldg(p.v[c] + eb); un[3 + c] = __ldg(p.vb[c] + eb); }
-  }
+    for (int j = 0; j < 4; j++) {
+      const int tk = warp + C::NWARP * j, kind = tk / 24, r = tk - 24 * kind, fo = r >> 3, t = r & 7;
+      const double* src = (kind < 2 ? p.vb[fo] : p.v[fo]) + ebase + 8 * pg + 64 * t + q;
+      uf0[j] = ldg_pinned(src); uf1[j] = ldg_pinned(src + 4);
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < 4; j++) { uf0[j] = 0.0; uf1[j] = 0.0; }
+  if ((int)blockIdx.x < p.nelem) load_f1_fragments((size_t)elem_of(blockIdx.x) * N);
   __syncthreads();
 
   for (int it = blockIdx.x; it < p.nelem; it += gridDim.x) {
     const int e = elem_of(it);
     const size_t eb = (size_t)e * N, ebd = (size_t)e * ND;
     double ep_bm = 0.0, ep_rho = 0.0, ep_f[3] = {0.0, 0.0, 0.0};
-    if (gth) {
-#pragma unroll
-      for (int f = 0; f < 6; f++) sm[f * AS + goff] = un[f];
-    }
     if (tid < 9) adv_l2_prefetch(p.G[tid] + ebd, ND * 8);
-    __syncthreads();
 
     // ---- F1: r axis.  batch (m, n): tile t = n, entry g = row m = pi(g); output a = 2q, 2q+1 (+8 nt): matrix as B ---
-    // 72 equal tasks (4 per warp): base flow A1 = J_r U -> DT array, A2 = DJ_r U -> DR array, adjoint velocity in place
+    // 72 equal tasks (4 per warp): base flow A1 = J_r U -> DT array, A2 = DJ_r U -> DR array, adjoint velocity -> TV;
+    // the data fragments were loaded from global memory one element ahead (no staging of the GLL fields, no barrier)
     {
       double mj[4], md[4];
 #pragma unroll
       for (int x = 0; x < 4; x++) { mj[x] = FT[(14 + x) * 32 + lane]; md[x] = FT[(18 + x) * 32 + lane]; }
-      // the four tasks of a warp: all fragment loads first, then the DMMAs (short dependent chains otherwise)
-      double d0[4], d1[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int tk = warp + C::NWARP * j, kind = tk / 24, r = tk - 24 * kind, fo = r >> 3, t = r & 7;
-        const double* src = sm + (kind < 2 ? 3 + fo : fo) * AS + 12 * pg + PS * t;
-        d0[j] = src[q]; d1[j] = src[4 + q];
-      }
-      __syncwarp();                                    // in place (kind 2): every lane has read before any lane stores
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int tk = warp + C::NWARP * j, kind = tk / 24, r = tk - 24 * kind, fo = r >> 3, t = r & 7;
@@ -189,8 +184,8 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           double c0 = 0.0, c1 = 0.0;
-          dmma884(c0, c1, d0[j], kind == 1 ? md[nt * 2 + 0] : mj[nt * 2 + 0]);
-          dmma884(c0, c1, d1[j], kind == 1 ? md[nt * 2 + 1] : mj[nt * 2 + 1]);
+          dmma884(c0, c1, uf0[j], kind == 1 ? md[nt * 2 + 0] : mj[nt * 2 + 0]);
+          dmma884(c0, c1, uf1[j], kind == 1 ? md[nt * 2 + 1] : mj[nt * 2 + 1]);
           if (nt == 0 || q < 2) st2(dst + 8 * nt + 2 * q, c0, c1);
         }
       }
@@ -376,7 +371,7 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
       __syncwarp();
     }
 
-    double pv0, pv1, pv2, b0, b1, b2;    // this element's GLL values for the epilogue
+    double pv0 = 0.0, pv1 = 0.0, pv2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;    // this element's GLL values for the epilogue
     {
       double jt[3], djt[3];    // J^T, DJ^T as A operand with output row pi(g)
 #pragma unroll
@@ -414,22 +409,23 @@ advop_mma_kernel(const __grid_constant__ AdvMmaParams p) {
         }
       }
       __syncthreads();
-      // epilogue inputs and the next element's fields travel during T2 / T3 (pinned: the compiler would sink them)
-      pv0 = un[0]; pv1 = un[1]; pv2 = un[2]; b0 = un[3]; b1 = un[4]; b2 = un[5];
+      // epilogue inputs of this element and F1's fragments of the next one travel during T2 / T3 (pinned: the compiler
+      // would sink them)
       if (gth) {
+        const size_t gi = eb + tid;
         if (flags & FLAG_ACCUM) {
 #pragma unroll
-          for (int c = 0; c < 3; c++) ep_f[c] = ld_pinned_rw(p.f[c] + eb + tid);
+          for (int c = 0; c < 3; c++) ep_f[c] = ld_pinned_rw(p.f[c] + gi);
         } else {
-          if (flags & (FLAG_SOURCES | FLAG_FSTATIC)) ep_bm = ldg_pinned(p.B + eb + tid);
-          if (flags & FLAG_SOURCES) ep_rho = ldg_pinned(p.rho + eb + tid);
-        }
-        if (it + (int)gridDim.x < p.nelem) {
-          const size_t nb = (size_t)elem_of(it + gridDim.x) * N + tid;
-#pragma unroll
-          for (int c = 0; c < 3; c++) { un[c] = ldg_pinned(p.v[c] + nb); un[3 + c] = ldg_pinned(p.vb[c] + nb); }
+          if (flags & (FLAG_SOURCES | FLAG_FSTATIC)) ep_bm = ldg_pinned(p.B + gi);
+          if (flags & FLAG_SOURCES) ep_rho = ldg_pinned(p.rho + gi);
+          if (flags & (FLAG_SOURCES | FLAG_SENS)) {
+            pv0 = ldg_pinned(p.v[0] + gi); pv1 = ldg_pinned(p.v[1] + gi); pv2 = ldg_pinned(p.v[2] + gi);
+            b0 = ldg_pinned(p.vb[0] + gi); b1 = ldg_pinned(p.vb[1] + gi); b2 = ldg_pinned(p.vb[2] + gi);
+          }
         }
       }
+      if (it + (int)gridDim.x < p.nelem) load_f1_fragments((size_t)elem_of(it + gridDim.x) * N);
 
       // ---- T2: s axis, K = 12.  batch beta = i + 12 n (96); output m = pi(g).  part 0: Y1 -> R, part 1: Y2 -> Fr -----
       // 36 (component, tile) pairs x {Y1: 6 DMMAs, Y2: 3}: every warp takes two pairs whole (18 DMMAs each warp), all

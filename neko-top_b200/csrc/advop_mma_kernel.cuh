@@ -6,8 +6,8 @@
 // per element; ncu r02h: issue 25 %, fp64 pipe 26 %, 45 % of the shared-memory wavefront peak) because every DFMA of
 // an r/s contraction needs its own shared-memory operand.  A DMMA takes one 64-bit fragment load per 256 FMAs, needs
 // ~60 registers per warp instead of 168, and so 18 warps share one SM with the whole element (15 fine-grid arrays)
-// in shared memory.  Measured (profiles/r02D, r02G, r02J): fused dealiased step 6.55 -> 2.75 ms at 32^3 elements (2.56 ->
-// 6.10 GDOF/s), un-fused drop-in 5.77 -> 2.68 ms.
+// in shared memory.  Measured (profiles/r02D, r02G, r02J, r02K): fused dealiased step 6.55 -> 2.69 ms at 32^3 elements
+// (2.56 -> 6.24 GDOF/s), un-fused drop-in 5.77 -> 2.58 ms.
 //
 // Formulation.  With J (12x8) the GLL -> Gauss-Legendre interpolation, D (12x12) the fine-grid derivative and
 // DJ = D J (12x8, formed on the host), per element:
@@ -35,13 +35,15 @@
 // Shared memory: 15 arrays [k][j][i] with row stride 12 and plane stride 148 doubles (148 = 4 mod 16: the four
 // contraction indices of a t-stage fragment load fall into different banks), 220 KB with the fragment tables; one CTA
 // of 18 warps per SM (96 registers).  Stages per element, separated by CTA barriers:
-//   load | F1 | F2 | F3 -> point-wise -> T1 (one 8-column tile per warp: these three only couple the 12 planes of a
-//   column, so there is no CTA barrier inside) | T2 | T3 | epilogue (one GLL point per thread).
+//   F1 (data fragments straight from global memory, loaded one element ahead) | F2 | F3 -> point-wise -> T1 (one
+//   8-column tile per warp: these three only couple the 12 planes of a column, so there is no CTA barrier inside) |
+//   T2 | T3 | epilogue (one GLL point per thread).
 // The matrix fragments sit in registers for a whole stage (re-loading them per tile was 45 % of the load wavefronts);
-// the epilogue's inputs and the next element's fields are loaded two stages early with volatile loads; the fine-grid
-// geometry of the element is prefetched into L2 when the element starts.  ncu (r02D5): DMMA pipe 45 % busy, shared-
-// memory wavefronts 43 %; the rest is the point-wise phase (21 %, LSU-bound: 27 shared + 9 global accesses per point)
-// and barrier waits (18 %: 18 tiles over 4 schedulers, 24 tasks over 18 warps in T3).
+// in the small stages a warp loads the fragments of all its tasks before the first DMMA; the epilogue's inputs and the
+// next element's F1 fragments are loaded two stages early with volatile loads; the fine-grid geometry of the element
+// is prefetched into L2 when the element starts.  ncu (r02J): DMMA pipe 49 % busy, shared-memory wavefronts 52 %; the
+// rest is the point-wise phase (21 %, bound by shared-memory / L1 wavefronts: 27 shared + 9 global 8-byte accesses per
+// point) and barrier waits (18 tiles and 18 warps over 4 schedulers: two schedulers carry 25 % more tensor work).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -113,3 +113,23 @@ def test_tile_order_is_a_permutation_with_short_reach():
     assert pos[e(0, 1, 0)] - pos[e(0, 0, 0)] == 4
     assert pos[e(0, 0, 1)] - pos[e(0, 0, 0)] == 16
     assert pos[e(4, 0, 0)] - pos[e(0, 0, 0)] == 16 * 5          # next tile column
+
+
+def test_composite_dealias_matrix_identities():
+    """What the tensor-core dealiased kernel (csrc/advop_mma_kernel.cuh) relies on: DJ = D_fine J differentiates AND
+    interpolates along an axis in one product.  Checked on polynomials up to the GLL degree (exact for them): DJ u =
+    u'(fine points); D_fine J = J D_gll (both are the derivative of the GLL interpolant at the fine points); the
+    rows of J sum to one.  Every order the library instantiates."""
+    from neko_top_b200 import sem
+    for lx in range(4, 11):
+        ds = sem.DealiasSpace(lx)
+        zg, _ = sem.zwgll(lx)
+        J, Dd = ds.interp, ds.dxd
+        DJ = Dd @ J
+        assert J.shape == (ds.lxd, lx) and np.allclose(J.sum(axis=1), 1.0, atol=1e-13)
+        assert np.allclose(DJ, J @ sem.dgll(zg), atol=1e-11 * lx)
+        for deg in range(lx):
+            u = zg ** deg
+            du = deg * ds.zd ** (deg - 1) if deg > 0 else np.zeros(ds.lxd)
+            assert np.allclose(J @ u, ds.zd ** deg, atol=1e-12)
+            assert np.allclose(DJ @ u, du, atol=1e-10)

@@ -23,8 +23,8 @@ for ln in sass.splitlines():
     if m and cur:
         kern[cur][m.group(1)] += 1
 KEY = ["DMMA", "DFMA", "UBLKCP", "UBLKPF", "SYNCS", "LDG.E.128", "LDG.E.64", "STG.E.128", "STG.E.64", "LDS.128",
-       "LDS.64", "LDC", "BAR", "SHFL", "ATOMG", "RED"]
-only = sys.argv[1:] or ["adjrhs_v3_kernel", "adjrhs_v2_kernel", "advop_kernel", "gs_op_kernel", "gs_face_pass_kernel",
+       "LDS.64", "STS.128", "LDC", "BAR", "SHFL", "ATOMG", "RED"]
+only = sys.argv[1:] or ["adjrhs_v3_kernel", "adjrhs_v2_kernel", "advop_mma_kernel", "advop_kernel", "gs_op_kernel", "gs_face_pass_kernel",
                         "helm_kernel", "deriv_kernel"]
 print(f"# SASS opcode counts per kernel (static), {os.path.basename(so)}, sm_100a; cuobjdump -sass")
 print("# " + "  ".join(KEY) + "  | total")

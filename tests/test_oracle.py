@@ -103,6 +103,34 @@ def test_dealiased_advection_matches_twin(oracle, lx, lxd):
         assert rel_l2(fc[c], fn[c].reshape(-1)) < 1e-12
 
 
+def test_composite_matrix_formulation_of_the_dealiased_operator(oracle):
+    """The formulation the tensor-core kernel evaluates (csrc/advop_mma_kernel.cuh), written out in numpy: with
+    DJ = D_fine J, forward T = (J x J x J) q and d_r U = (DJ x J x J) U ..., backward out = (J^T x J^T x J^T) R +
+    (DJ^T x J^T x J^T) Fr + (J^T x DJ^T x J^T) Fs + (J^T x J^T x DJ^T) Ft.  Must equal the oracle's dealiased adjoint
+    operator (interpolate, opgrad on the fine grid, cdtp, project: adv_adjoint_dealias.f90:358-456) to rounding."""
+    from neko_top_b200 import sem
+    lx, lxd = 8, 12
+    P = Problem(lx, ne=(2, 1, 2), deform=0.03)
+    ds = sem.DealiasSpace(lx, lxd)
+    J, DJ, wd = ds.interp, ds.dxd @ ds.interp, ds.wd
+    A = lambda a: np.asarray(a, dtype=np.float64).reshape(P.nelv, lx, lx, lx)              # [e, k, j, i]
+    ap = lambda Mr, Ms, Mt, q: np.einsum("ai,bj,ck,ekji->ecba", Mr, Ms, Mt, q, optimize=True)   # fine [e, c, b, a]
+    bk = lambda Mr, Ms, Mt, q: np.einsum("ai,bj,ck,ecba->ekji", Mr, Ms, Mt, q, optimize=True)   # transposed
+    v, ub, G = [A(a) for a in P.v], [A(a) for a in P.ub], [ap(J, J, J, A(g)) for g in P.G]
+    tv, tb = [ap(J, J, J, a) for a in v], [ap(J, J, J, a) for a in ub]
+    dU = [(ap(DJ, J, J, a), ap(J, DJ, J, a), ap(J, J, DJ, a)) for a in ub]
+    w3 = np.einsum("c,b,a->cba", wd, wd, wd)[None]
+    R = [sum(tv[c] * w3 * (G[3 * d] * dU[c][0] + G[3 * d + 1] * dU[c][1] + G[3 * d + 2] * dU[c][2]) for c in range(3))
+         for d in range(3)]
+    cr, cs, ct = (w3 * sum(tb[k] * G[3 * k + e] for k in range(3)) for e in range(3))
+    rng = np.random.default_rng(12)
+    f0 = [rng.standard_normal(P.n) for _ in range(3)]
+    fo = oracle.adjoint_advection_dealias(f0, P.v, P.ub, lx, lxd, P.nelv, P.G)
+    for c in range(3):
+        out = bk(J, J, J, R[c]) + bk(DJ, J, J, tv[c] * cr) + bk(J, DJ, J, tv[c] * cs) + bk(J, J, DJ, tv[c] * ct)
+        assert rel_l2(f0[c] - out.reshape(-1), fo[c]) < 1e-13
+
+
 def test_full_rhs_matches_twin(oracle):
     P = Problem(6, ne=(2, 2, 2), deform=0.03)
     rng = np.random.default_rng(7)
